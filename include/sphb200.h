@@ -1,0 +1,178 @@
+/* sphb200.h -- C ABI of the B200-native SPH step pipeline.
+ *
+ * Drop-in boundary for the hot path of DanielaCourel/smoothed_particle_hydrodynamics:
+ * the per-timestep pipeline behind `class SPH` (reference src/sph.h:15-215,
+ * src/sph.cpp:190-304).  The reference has no FFI layer -- the C++ class IS the
+ * seam -- so this header is what the C++ facade
+ * (smoothed_particle_hydrodynamics_b200/host/sph.h, same public interface as the
+ * reference's SPH) binds to.  Plain pointers and sizes only; no torch, no Qt.
+ *
+ * Every entry point returns 0 on success and a negative SPHB200_E_* code on
+ * failure; sphb200_last_error() gives the message.  There is NO CPU fallback:
+ * without a CUDA device sphb200_create fails with SPHB200_E_CUDA.
+ *
+ * Threading: one context = one CUDA device + one stream; calls on a context
+ * must not overlap (the reference never re-enters step() either, sph.cpp:171).
+ */
+#ifndef SPHB200_H
+#define SPHB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHB200_VERSION 1
+
+enum
+{
+   SPHB200_OK = 0,
+   SPHB200_E_INVALID = -1,   /* bad argument / bad state                       */
+   SPHB200_E_CUDA = -2,      /* CUDA runtime error or no device                */
+   SPHB200_E_CAPACITY = -3,  /* particle / neighbour capacity exceeded         */
+   SPHB200_E_COMM = -4       /* NCCL error (multi-GPU slabs)                   */
+};
+
+/* neighbour policy */
+enum
+{
+   /* bit-for-bit the reference's findNeighbors sub-sampler (sph.cpp:484-692) */
+   SPHB200_NEIGHBORS_REFERENCE_SAMPLED = 0,
+   /* every particle within h (27 fine cells of edge h); feeds the same
+    * computeDensity / computeAcceleration / integrate formulas */
+   SPHB200_NEIGHBORS_FULL = 1
+};
+
+/* Every literal of SPH::SPH() (sph.cpp:36-118) plus the
+ * switches the reference lacks.  sphb200_default_params() fills the reference
+ * values.  Fields marked [rt] may be changed between steps with
+ * sphb200_set_params (the reference's setters, sph.cpp:1225-1289); the others
+ * are fixed at sphb200_create. */
+typedef struct SphParams
+{
+   int particle_count;        /* mParticleCount (M*1024, sph.cpp:59)           */
+   int grid_x, grid_y, grid_z;/* voxels per axis, edge 2h (sph.cpp:60-62)      */
+   int examine_count;         /* mExamineCount E (sph.cpp:98); list capacity   */
+   int neighbor_mode;         /* SPHB200_NEIGHBORS_*                            */
+   int use_uniform_gravity;   /* [rt] 0 = reference (mGravity is inert, F7)    */
+   int use_wall_collision;    /* [rt] 0 = reference (dead code, F6)            */
+   float h;                   /* sph.cpp:47                                     */
+   float simulation_scale;    /* sph.cpp:48                                     */
+   float time_step;           /* [rt] sph.cpp:70                               */
+   float rho0;                /* [rt] sph.cpp:74                               */
+   float stiffness;           /* [rt] sph.cpp:75                               */
+   float viscosity;           /* [rt] sph.cpp:77                               */
+   float damping;             /* [rt] sph.cpp:78                               */
+   float cfl_limit;           /* [rt] sph.cpp:89                               */
+   float grav_constant;       /* [rt] sph.cpp:80                               */
+   float central_mass;        /* [rt] sph.cpp:81                               */
+   float central_pos[3];      /* [rt] sph.cpp:83-85; all <0 => box centre      */
+   float softening;           /* [rt] sph.cpp:86;  <0 => h*scale               */
+   float gravity[3];          /* [rt] sph.cpp:76                               */
+   /* engine knobs (no reference counterpart) */
+   int kernel_variant;        /* FULL mode: 0 = auto (tiled), 1 = untiled      */
+   int enable_timers;         /* [rt] CUDA-event phase timers (updateElapsed)  */
+   int reserved[6];
+} SphParams;
+
+/* constants the constructor derives (sph.cpp:51-57, 64-67, 90, 93-95) */
+typedef struct SphDerived
+{
+   float h2, h_times2, h_times2_inv, h_scaled, h_scaled2, h_scaled6, h_scaled9;
+   float kernel1, kernel2, kernel3;
+   float cell_size, max_x, max_y, max_z;
+   float cfl_limit2;
+   float central_pos[3], softening;
+   int grid_cell_count;
+   int total_steps;           /* round(1.0 / time_step), sph.cpp:69-71         */
+} SphDerived;
+
+/* fields of sphb200_download(); layouts are the reference's host layouts */
+enum
+{
+   SPHB200_F_POSITION = 0,        /* float[3N]  Particle::mPosition (particle.h:15)   */
+   SPHB200_F_VELOCITY = 1,        /* float[3N]  Particle::mVelocity                   */
+   SPHB200_F_MASS = 2,            /* float[N]   Particle::mMass                       */
+   SPHB200_F_DENSITY = 3,         /* float[N]   Particle::mDensity (last step)        */
+   SPHB200_F_ACCELERATION = 4,    /* float[3N]  Particle::mAcceleration (last step)   */
+   SPHB200_F_NEIGHBOR_COUNT = 5,  /* int[N]     Particle::mNeighborCount              */
+   SPHB200_F_VOXEL_ID = 6,        /* int[N]     SPH::mVoxelIds  (sph.h:143)           */
+   SPHB200_F_VOXEL_COORD = 7,     /* int[3N]    SPH::mVoxelCoords (sph.h:144)         */
+   SPHB200_F_GRID_START = 8,      /* int[cells+1] CSR offsets of SPH::mGrid lists     */
+   SPHB200_F_GRID_MEMBERS = 9,    /* uint32[N]  mGrid[c] contents, in push_back order */
+   SPHB200_F_CELL_COUNT = 10,     /* int[cells] mGrid[c].count() (visualization.cpp:193) */
+   SPHB200_F_NEIGHBOR_INDEX = 11, /* uint32[N*E] SPH::mNeighbors (sph.h:173)          */
+   SPHB200_F_NEIGHBOR_DISTANCE = 12, /* float[N*E] SPH::mNeighborDistancesScaled      */
+   SPHB200_F_FINE_KEY = 13        /* int[N]     FULL mode fine-cell key               */
+};
+
+typedef struct sphb200_ctx sphb200_ctx;
+
+/* ---- lifetime: SPH::SPH() / ~SPH() (sph.cpp:36-125) ------------------------ */
+int sphb200_default_params(SphParams* p);
+int sphb200_derive(const SphParams* p, SphDerived* out);
+/* device < 0: current device.  Allocates all HBM buffers; state is zero. */
+int sphb200_create(const SphParams* p, int device, sphb200_ctx** out);
+int sphb200_destroy(sphb200_ctx* ctx);
+const char* sphb200_last_error(const sphb200_ctx* ctx);   /* ctx may be NULL */
+
+/* ---- configuration: the setters of sph.cpp:1225-1289 ----------------------- */
+int sphb200_get_params(const sphb200_ctx* ctx, SphParams* out);
+int sphb200_set_params(sphb200_ctx* ctx, const SphParams* p);   /* [rt] fields only */
+int sphb200_get_derived(const sphb200_ctx* ctx, SphDerived* out);
+/* run on a caller-owned CUDA stream (cudaStream_t as void*); NULL = own stream */
+int sphb200_set_stream(sphb200_ctx* ctx, void* cuda_stream);
+
+/* ---- scenes (host generators; initParticlePolitionsSphere, sph.cpp:361-425) */
+/* the constructor's seeded rotating sphere, bit-identical (glibc rand()) */
+int sphb200_scene_sphere(const SphParams* p, float* pos_xyz, float* vel_xyz);
+/* jittered cubic lattice (SURVEY 8(d) scene rule), ids first_id..first_id+count-1 */
+int sphb200_scene_lattice(int nx, int ny, int nz, float spacing, const float origin[3],
+                          uint32_t seed, long long first_id, long long count, float* pos_xyz);
+
+/* ---- state: host <-> HBM (Particle arrays, particle.h:13-18) ----------------- */
+/* xyz-interleaved host arrays of particle_count entries; mass may be NULL (=1) */
+int sphb200_upload_state(sphb200_ctx* ctx, const float* pos_xyz, const float* vel_xyz, const float* mass);
+int sphb200_download(sphb200_ctx* ctx, int field, void* dst, size_t dst_bytes);
+
+/* ---- the hot path: SPH::step() (sph.cpp:190-304) ---------------------------- */
+/* n_steps device-resident steps; asynchronous on the context's stream */
+int sphb200_step(sphb200_ctx* ctx, int n_steps);
+int sphb200_synchronize(sphb200_ctx* ctx);
+/* one reference-style step on HOST buffers: upload, step, download pos+vel
+ * (what SPH::step() does to Particle::mPosition / mVelocity in place) */
+int sphb200_step_host(sphb200_ctx* ctx, float* pos_xyz, float* vel_xyz, const float* mass);
+/* FULL mode only: materialise mNeighbors / mNeighborDistancesScaled for the
+ * LAST step's pre-step positions (the hot kernels never store lists) */
+int sphb200_build_neighbor_lists(sphb200_ctx* ctx);
+
+/* ---- per-step scalars ------------------------------------------------------- */
+/* mKineticEnergyTotal / mPotentialEnergyTotal of the last step (sph.cpp:1004-1007) */
+int sphb200_get_energies(sphb200_ctx* ctx, float* e_kin, float* e_pot);
+/* sum / max / min of mNeighborCount of the last step (sph.cpp:226-232) */
+int sphb200_get_neighbor_stats(sphb200_ctx* ctx, long long* total, int* max_count, int* min_count);
+/* ms of the last step: voxelize, findNeighbors, density, pressure, acceleration,
+ * integrate -- the six slots of SPH::updateElapsed (sph.h:73-81) */
+int sphb200_get_timings(sphb200_ctx* ctx, float ms[6]);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+int sphb200_get_launch_count(const sphb200_ctx* ctx, long long* launches);
+
+/* ---- multi-GPU slabs along z (net-new) ------------------------- */
+/* 128-byte NCCL unique id for bootstrap through the caller's own channel */
+int sphb200_comm_unique_id(void* id128);
+/* this context becomes slab `rank` of `nranks` (owns voxel layers
+ * [z0, z1) of the global grid); particle_count is the slab CAPACITY */
+int sphb200_comm_init(sphb200_ctx* ctx, int rank, int nranks, const void* id128, int z0, int z1);
+int sphb200_get_local_count(const sphb200_ctx* ctx, int* owned, int* ghosts);
+/* upload `count` owned particles with their global ids (slab mode) */
+int sphb200_upload_slab(sphb200_ctx* ctx, int count, const float* pos_xyz, const float* vel_xyz,
+                        const float* mass, const uint32_t* global_ids);
+int sphb200_download_slab(sphb200_ctx* ctx, int field, void* dst, size_t dst_bytes, uint32_t* global_ids,
+                          int* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHB200_H */

@@ -1,0 +1,13 @@
+"""B200-native SPH step pipeline (drop-in for the hot path of
+DanielaCourel/smoothed_particle_hydrodynamics, reference src/sph.cpp:190-304).
+
+The product is the C-ABI shared library ``libsphb200.so`` (include/sphb200.h:
+hand-written CUDA for sm_100a) and the C++ ``SPH`` facade in ``host/``.  This
+package is the ctypes binding used by tests, bench.py and the smoke test; it
+contains no compute and no CPU fallback -- without the built library or without
+a CUDA device every entry point raises.
+"""
+from .binding import (  # noqa: F401
+    FULL, SAMPLED, SPH, Field, SphDerived, SphError, SphParams, default_params, derive, lib, lib_path,
+    scene_lattice, scene_sphere,
+)

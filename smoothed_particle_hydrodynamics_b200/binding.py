@@ -1,0 +1,387 @@
+"""ctypes binding of include/sphb200.h + a Python mirror of the reference's
+``class SPH`` public interface (src/sph.h:20-84) for tests and benchmarks."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+SAMPLED, FULL = 0, 1
+
+
+class SphError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("sphb200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class SphParams(C.Structure):
+    _fields_ = [
+        ("particle_count", C.c_int),
+        ("grid_x", C.c_int), ("grid_y", C.c_int), ("grid_z", C.c_int),
+        ("examine_count", C.c_int),
+        ("neighbor_mode", C.c_int),
+        ("use_uniform_gravity", C.c_int),
+        ("use_wall_collision", C.c_int),
+        ("h", C.c_float),
+        ("simulation_scale", C.c_float),
+        ("time_step", C.c_float),
+        ("rho0", C.c_float),
+        ("stiffness", C.c_float),
+        ("viscosity", C.c_float),
+        ("damping", C.c_float),
+        ("cfl_limit", C.c_float),
+        ("grav_constant", C.c_float),
+        ("central_mass", C.c_float),
+        ("central_pos", C.c_float * 3),
+        ("softening", C.c_float),
+        ("gravity", C.c_float * 3),
+        ("kernel_variant", C.c_int),
+        ("enable_timers", C.c_int),
+        ("reserved", C.c_int * 6),
+    ]
+
+
+class SphDerived(C.Structure):
+    _fields_ = [
+        ("h2", C.c_float), ("h_times2", C.c_float), ("h_times2_inv", C.c_float),
+        ("h_scaled", C.c_float), ("h_scaled2", C.c_float), ("h_scaled6", C.c_float), ("h_scaled9", C.c_float),
+        ("kernel1", C.c_float), ("kernel2", C.c_float), ("kernel3", C.c_float),
+        ("cell_size", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float), ("max_z", C.c_float),
+        ("cfl_limit2", C.c_float),
+        ("central_pos", C.c_float * 3), ("softening", C.c_float),
+        ("grid_cell_count", C.c_int),
+        ("total_steps", C.c_int),
+    ]
+
+
+class Field:
+    POSITION, VELOCITY, MASS, DENSITY, ACCELERATION, NEIGHBOR_COUNT, VOXEL_ID, VOXEL_COORD = range(8)
+    GRID_START, GRID_MEMBERS, CELL_COUNT, NEIGHBOR_INDEX, NEIGHBOR_DISTANCE, FINE_KEY = range(8, 14)
+
+
+# every symbol include/sphb200.h declares: (name, argtypes, restype)
+_VP = C.c_void_p
+API = [
+    ("sphb200_default_params", [C.POINTER(SphParams)], C.c_int),
+    ("sphb200_derive", [C.POINTER(SphParams), C.POINTER(SphDerived)], C.c_int),
+    ("sphb200_create", [C.POINTER(SphParams), C.c_int, C.POINTER(_VP)], C.c_int),
+    ("sphb200_destroy", [_VP], C.c_int),
+    ("sphb200_last_error", [_VP], C.c_char_p),
+    ("sphb200_get_params", [_VP, C.POINTER(SphParams)], C.c_int),
+    ("sphb200_set_params", [_VP, C.POINTER(SphParams)], C.c_int),
+    ("sphb200_get_derived", [_VP, C.POINTER(SphDerived)], C.c_int),
+    ("sphb200_set_stream", [_VP, _VP], C.c_int),
+    ("sphb200_scene_sphere", [C.POINTER(SphParams), _VP, _VP], C.c_int),
+    ("sphb200_scene_lattice", [C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_float), C.c_uint32,
+                               C.c_longlong, C.c_longlong, _VP], C.c_int),
+    ("sphb200_upload_state", [_VP, _VP, _VP, _VP], C.c_int),
+    ("sphb200_download", [_VP, C.c_int, _VP, C.c_size_t], C.c_int),
+    ("sphb200_step", [_VP, C.c_int], C.c_int),
+    ("sphb200_synchronize", [_VP], C.c_int),
+    ("sphb200_step_host", [_VP, _VP, _VP, _VP], C.c_int),
+    ("sphb200_build_neighbor_lists", [_VP], C.c_int),
+    ("sphb200_get_energies", [_VP, C.POINTER(C.c_float), C.POINTER(C.c_float)], C.c_int),
+    ("sphb200_get_neighbor_stats", [_VP, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+    ("sphb200_get_timings", [_VP, C.POINTER(C.c_float)], C.c_int),
+    ("sphb200_get_launch_count", [_VP, C.POINTER(C.c_longlong)], C.c_int),
+    ("sphb200_comm_unique_id", [_VP], C.c_int),
+    ("sphb200_comm_init", [_VP, C.c_int, C.c_int, _VP, C.c_int, C.c_int], C.c_int),
+    ("sphb200_get_local_count", [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
+    ("sphb200_upload_slab", [_VP, C.c_int, _VP, _VP, _VP, _VP], C.c_int),
+    ("sphb200_download_slab", [_VP, C.c_int, _VP, C.c_size_t, _VP, C.POINTER(C.c_int)], C.c_int),
+]
+
+
+def lib_path():
+    return os.path.join(_HERE, "libsphb200.so")
+
+
+_lib = None
+
+
+def lib():
+    """Loads libsphb200.so (built by `python -m smoothed_particle_hydrodynamics_b200.build`).
+    Fails loudly when it is missing: there is no other implementation to fall back to."""
+    global _lib
+    if _lib is None:
+        path = lib_path()
+        if not os.path.exists(path):
+            raise SphError(-2, "%s is missing: run `python -m smoothed_particle_hydrodynamics_b200.build` "
+                               "(there is no CPU fallback)" % path)
+        L = C.CDLL(path)
+        for name, args, res in API:
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = res
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def default_params(**kw):
+    p = SphParams()
+    rc = lib().sphb200_default_params(C.byref(p))
+    if rc:
+        raise SphError(rc, "default_params")
+    _apply(p, kw)
+    return p
+
+
+def _apply(p, kw):
+    for k, v in kw.items():
+        if k in ("central_pos", "gravity"):
+            arr = getattr(p, k)
+            for i in range(3):
+                arr[i] = float(v[i])
+        elif k == "grid":
+            p.grid_x, p.grid_y, p.grid_z = [int(g) for g in v]
+        else:
+            if not hasattr(p, k):
+                raise AttributeError("SphParams has no field %r" % k)
+            setattr(p, k, v)
+
+
+def derive(p):
+    d = SphDerived()
+    rc = lib().sphb200_derive(C.byref(p), C.byref(d))
+    if rc:
+        raise SphError(rc, lib().sphb200_last_error(None).decode())
+    return d
+
+
+def scene_sphere(p):
+    """initParticlePolitionsSphere (sph.cpp:361-425): the constructor's scene."""
+    pos = np.empty((p.particle_count, 3), np.float32)
+    vel = np.empty((p.particle_count, 3), np.float32)
+    rc = lib().sphb200_scene_sphere(C.byref(p), _ptr(pos), _ptr(vel))
+    if rc:
+        raise SphError(rc, "scene_sphere")
+    return pos, vel
+
+
+def scene_lattice(nx, ny, nz, spacing, origin=(0.0, 0.0, 0.0), seed=42, first_id=0, count=None, out=None):
+    if count is None:
+        count = nx * ny * nz - first_id
+    pos = out if out is not None else np.empty((count, 3), np.float32)
+    org = (C.c_float * 3)(*[float(o) for o in origin])
+    rc = lib().sphb200_scene_lattice(nx, ny, nz, float(spacing), org, seed, first_id, count, _ptr(pos))
+    if rc:
+        raise SphError(rc, "scene_lattice: bad arguments")
+    return pos
+
+
+class Particle:
+    """Host mirror with the reference's member names (src/particle.h:13-18)."""
+
+    def __init__(self, n):
+        self.mMass = np.zeros(n, np.float32)
+        self.mDensity = np.zeros(n, np.float32)
+        self.mPosition = np.zeros(3 * n, np.float32)
+        self.mVelocity = np.zeros(3 * n, np.float32)
+        self.mAcceleration = np.zeros(3 * n, np.float32)
+        self.mNeighborCount = np.zeros(n, np.int32)
+
+
+class SPH:
+    """Python mirror of the reference's `class SPH` public interface
+    (src/sph.h:20-84) over the C ABI.  `SPH()` with no arguments is the
+    reference constructor: default parameters + the seeded sphere scene."""
+
+    def __init__(self, params=None, device=-1, init_scene=None, **kw):
+        self._lib = lib()
+        self._h = _VP()
+        p = params if params is not None else default_params()
+        _apply(p, kw)
+        rc = self._lib.sphb200_create(C.byref(p), device, C.byref(self._h))
+        if rc:
+            msg = self._lib.sphb200_last_error(self._h if self._h else None).decode()
+            if self._h:
+                self._lib.sphb200_destroy(self._h)
+                self._h = _VP()
+            raise SphError(rc, msg)
+        self._particles = Particle(p.particle_count)
+        if init_scene is None:
+            init_scene = params is None and not kw
+        if init_scene:
+            pos, vel = scene_sphere(p)
+            self.upload(pos, vel)
+
+    # ---- plumbing ---------------------------------------------------------
+    def _check(self, rc):
+        if rc:
+            raise SphError(rc, self._lib.sphb200_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            self._lib.sphb200_destroy(self._h)
+            self._h = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def params(self):
+        p = SphParams()
+        self._check(self._lib.sphb200_get_params(self._h, C.byref(p)))
+        return p
+
+    @property
+    def derived(self):
+        d = SphDerived()
+        self._check(self._lib.sphb200_get_derived(self._h, C.byref(d)))
+        return d
+
+    def set_params(self, **kw):
+        p = self.params
+        _apply(p, kw)
+        self._check(self._lib.sphb200_set_params(self._h, C.byref(p)))
+
+    def set_stream(self, cuda_stream):
+        self._check(self._lib.sphb200_set_stream(self._h, _VP(cuda_stream) if cuda_stream else None))
+
+    def upload(self, pos, vel, mass=None):
+        n = self.params.particle_count
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1)
+        vel = np.ascontiguousarray(vel, np.float32).reshape(-1)
+        assert pos.size == 3 * n and vel.size == 3 * n, (pos.size, vel.size, n)
+        if mass is not None:
+            mass = np.ascontiguousarray(mass, np.float32).reshape(-1)
+            assert mass.size == n
+        self._check(self._lib.sphb200_upload_state(self._h, _ptr(pos), _ptr(vel), _ptr(mass)))
+
+    def upload_ptr(self, pos_ptr, vel_ptr, mass_ptr=None):
+        self._check(self._lib.sphb200_upload_state(self._h, _VP(pos_ptr), _VP(vel_ptr),
+                                                   _VP(mass_ptr) if mass_ptr else None))
+
+    def step_host_ptr(self, pos_ptr, vel_ptr, mass_ptr=None):
+        self._check(self._lib.sphb200_step_host(self._h, _VP(pos_ptr), _VP(vel_ptr),
+                                                _VP(mass_ptr) if mass_ptr else None))
+
+    def download(self, field):
+        p = self.params
+        n, E = p.particle_count, p.examine_count
+        cells = p.grid_x * p.grid_y * p.grid_z
+        shape, dt = {
+            Field.POSITION: ((n, 3), np.float32), Field.VELOCITY: ((n, 3), np.float32),
+            Field.MASS: ((n,), np.float32), Field.DENSITY: ((n,), np.float32),
+            Field.ACCELERATION: ((n, 3), np.float32), Field.NEIGHBOR_COUNT: ((n,), np.int32),
+            Field.VOXEL_ID: ((n,), np.int32), Field.VOXEL_COORD: ((n, 3), np.int32),
+            Field.GRID_START: ((cells + 1,), np.int32), Field.GRID_MEMBERS: ((n,), np.uint32),
+            Field.CELL_COUNT: ((cells,), np.int32), Field.NEIGHBOR_INDEX: ((n, E), np.uint32),
+            Field.NEIGHBOR_DISTANCE: ((n, E), np.float32), Field.FINE_KEY: ((n,), np.int32),
+        }[field]
+        out = np.empty(shape, dt)
+        self._check(self._lib.sphb200_download(self._h, field, _ptr(out), out.nbytes))
+        return out
+
+    def step_n(self, n_steps):
+        """n device-resident steps, asynchronous (sphb200_step)."""
+        self._check(self._lib.sphb200_step(self._h, int(n_steps)))
+
+    def synchronize(self):
+        self._check(self._lib.sphb200_synchronize(self._h))
+
+    def build_neighbor_lists(self):
+        self._check(self._lib.sphb200_build_neighbor_lists(self._h))
+
+    def energies(self):
+        ek, ep = C.c_float(), C.c_float()
+        self._check(self._lib.sphb200_get_energies(self._h, C.byref(ek), C.byref(ep)))
+        return ek.value, ep.value
+
+    def neighbor_stats(self):
+        t, mx, mn = C.c_longlong(), C.c_int(), C.c_int()
+        self._check(self._lib.sphb200_get_neighbor_stats(self._h, C.byref(t), C.byref(mx), C.byref(mn)))
+        return t.value, mx.value, mn.value
+
+    def timings_ms(self):
+        a = (C.c_float * 6)()
+        self._check(self._lib.sphb200_get_timings(self._h, a))
+        return list(a)
+
+    def launch_count(self):
+        v = C.c_longlong()
+        self._check(self._lib.sphb200_get_launch_count(self._h, C.byref(v)))
+        return v.value
+
+    # ---- the reference's public interface (src/sph.h:22-70) -----------------
+    def step(self):
+        """SPH::step() (sph.cpp:190-304): one step, then refresh the host mirror
+        the GL view reads (visualization.cpp:144-157)."""
+        self.step_n(1)
+        self._particles.mPosition[:] = self.download(Field.POSITION).reshape(-1)
+
+    def getParticles(self):
+        p = self._particles
+        p.mPosition[:] = self.download(Field.POSITION).reshape(-1)
+        p.mVelocity[:] = self.download(Field.VELOCITY).reshape(-1)
+        p.mMass[:] = self.download(Field.MASS)
+        p.mDensity[:] = self.download(Field.DENSITY)
+        p.mAcceleration[:] = self.download(Field.ACCELERATION).reshape(-1)
+        p.mNeighborCount[:] = self.download(Field.NEIGHBOR_COUNT)
+        return p
+
+    def getParticleCount(self):
+        return self.params.particle_count
+
+    def getGridCellCounts(self):
+        p = self.params
+        return p.grid_x, p.grid_y, p.grid_z
+
+    def getParticleBounds(self):
+        d = self.derived
+        return d.max_x, d.max_y, d.max_z
+
+    def getInteractionRadius2(self):
+        return self.derived.h_scaled2
+
+    def getCellSize(self):
+        return self.derived.cell_size
+
+    def getGrid(self):
+        """mGrid as (start, members): cell c holds members[start[c]:start[c+1]]."""
+        return self.download(Field.GRID_START), self.download(Field.GRID_MEMBERS)
+
+    def getGravity(self):
+        return tuple(self.params.gravity)
+
+    def setGravity(self, g):
+        self.set_params(gravity=g)
+
+    def getStiffness(self):
+        return self.params.stiffness
+
+    def setStiffness(self, v):
+        self.set_params(stiffness=v)
+
+    def getViscosityScalar(self):
+        return self.params.viscosity
+
+    def setViscosityScalar(self, v):
+        self.set_params(viscosity=v)
+
+    def getTimeStep(self):
+        return self.params.time_step
+
+    def setTimeStep(self, v):
+        self.set_params(time_step=v)
+
+    def getDamping(self):
+        return self.params.damping
+
+    def setDamping(self, v):
+        self.set_params(damping=v)
+
+    def getCflLimit(self):
+        return self.params.cfl_limit
+
+    def setCflLimit(self, v):
+        self.set_params(cfl_limit=v)

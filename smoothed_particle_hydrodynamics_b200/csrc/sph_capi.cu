@@ -1,0 +1,663 @@
+// sph_capi.cu -- the C ABI of include/sphb200.h: context lifetime, parameter
+// derivation (the reference constructor's own expressions), host<->HBM state
+// transfer, step dispatch and per-step scalars.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <limits>
+#include <new>
+
+#include "sph_internal.h"
+
+int sph_full_unsort(sphb200_ctx* ctx);
+int sph_full_tile_count(const sphb200_ctx* ctx);
+
+namespace
+{
+
+thread_local std::string g_error;   // errors raised without a context
+
+constexpr int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) k_pack_state(int n, const float* __restrict__ pos_xyz,
+                                                          const float* __restrict__ vel_xyz,
+                                                          const float* __restrict__ mass, float4* __restrict__ pos4,
+                                                          float4* __restrict__ vel4)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n)
+      return;
+   float m = mass ? mass[i] : 1.0f;
+   pos4[i] = make_float4(pos_xyz[3 * (size_t)i], pos_xyz[3 * (size_t)i + 1], pos_xyz[3 * (size_t)i + 2], m);
+   vel4[i] = make_float4(vel_xyz[3 * (size_t)i], vel_xyz[3 * (size_t)i + 1], vel_xyz[3 * (size_t)i + 2], 0.0f);
+}
+
+// float4 -> xyz-interleaved (Particle::mPosition layout, particle.h:15)
+__global__ void __launch_bounds__(kThreads) k_unpack_xyz(int n, const float4* __restrict__ src,
+                                                          float* __restrict__ dst_xyz)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n)
+      return;
+   float4 v = src[i];
+   dst_xyz[3 * (size_t)i] = v.x;
+   dst_xyz[3 * (size_t)i + 1] = v.y;
+   dst_xyz[3 * (size_t)i + 2] = v.z;
+}
+
+__global__ void __launch_bounds__(kThreads) k_unpack_w(int n, const float4* __restrict__ src, float* __restrict__ dst)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n)
+      dst[i] = src[i].w;
+}
+
+int blocks_for(int n) { return (n + kThreads - 1) / kThreads; }
+
+// SPH::SPH() (sph.cpp:47-95): same expressions, same types, same rounding.
+void derive(const SphParams& p, SphDerived& d)
+{
+   float h = p.h;
+   float scale = p.simulation_scale;
+   d.h2 = (float)pow((double)h, 2.0);
+   d.h_times2 = h * 2.0f;
+   d.h_times2_inv = 1.0f / d.h_times2;
+   d.h_scaled = h * scale;
+   d.h_scaled2 = (float)pow((double)(h * scale), 2.0);
+   d.h_scaled6 = (float)pow((double)(h * scale), 6.0);
+   d.h_scaled9 = (float)pow((double)(h * scale), 9.0);
+   d.grid_cell_count = p.grid_x * p.grid_y * p.grid_z;
+   d.cell_size = 2.0f * h;
+   d.max_x = d.cell_size * (float)p.grid_x;
+   d.max_y = d.cell_size * (float)p.grid_y;
+   d.max_z = d.cell_size * (float)p.grid_z;
+   d.total_steps = (int)round(1.0f / p.time_step);
+   if (p.central_pos[0] < 0.0f && p.central_pos[1] < 0.0f && p.central_pos[2] < 0.0f)
+   {
+      d.central_pos[0] = d.max_x * 0.5f;
+      d.central_pos[1] = d.max_y * 0.5f;
+      d.central_pos[2] = d.max_z * 0.5f;
+   }
+   else
+      for (int k = 0; k < 3; k++)
+         d.central_pos[k] = p.central_pos[k];
+   d.softening = p.softening < 0.0f ? d.h_scaled : p.softening;
+   d.cfl_limit2 = p.cfl_limit * p.cfl_limit;
+   d.kernel1 = 315.0f / (64.0f * (float)(M_PI) * d.h_scaled9);
+   d.kernel2 = -45.0f / ((float)(M_PI) * d.h_scaled6);
+   d.kernel3 = -d.kernel2;
+}
+
+int validate(const SphParams& p, std::string& why)
+{
+   if (p.particle_count < 0) { why = "particle_count < 0"; return 1; }
+   if (p.grid_x < 1 || p.grid_y < 1 || p.grid_z < 1) { why = "grid cells must be >= 1"; return 1; }
+   if ((long long)p.grid_x * p.grid_y * p.grid_z * 8ll >= (1ll << 31)) { why = "grid too large for 32-bit cell keys"; return 1; }
+   if (p.examine_count < 9) { why = "examine_count must be >= 9 (K=8 windows, sph.cpp:679)"; return 1; }
+   if (!(p.h > 0.0f)) { why = "h must be > 0"; return 1; }
+   if (!(p.simulation_scale > 0.0f)) { why = "simulation_scale must be > 0"; return 1; }
+   if (p.neighbor_mode != SPHB200_NEIGHBORS_REFERENCE_SAMPLED && p.neighbor_mode != SPHB200_NEIGHBORS_FULL)
+   {
+      why = "unknown neighbor_mode";
+      return 1;
+   }
+   if ((long long)p.particle_count * p.examine_count >= (1ll << 40)) { why = "neighbour table too large"; return 1; }
+   return 0;
+}
+
+template <typename T>
+cudaError_t dev_alloc(T** p, size_t count)
+{
+   return cudaMalloc((void**)p, sizeof(T) * (count ? count : 1));
+}
+
+int alloc_lists(sphb200_ctx* ctx)
+{
+   if (ctx->nbr_idx)
+      return SPHB200_OK;
+   size_t cap = (size_t)ctx->capacity * (size_t)ctx->params.examine_count;
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->nbr_idx, cap));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->nbr_dist, cap));
+   return SPHB200_OK;
+}
+
+int fetch_scalars(sphb200_ctx* ctx)
+{
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(&ctx->h_scalars, ctx->d_scalars, sizeof(StepScalars), cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+   return SPHB200_OK;
+}
+
+}  // namespace
+
+int sph_fail(sphb200_ctx* ctx, int code, const std::string& msg)
+{
+   if (ctx)
+      ctx->error = msg;
+   else
+      g_error = msg;
+   return code;
+}
+
+DevParams sph_dev_params(const sphb200_ctx* ctx)
+{
+   const SphParams& p = ctx->params;
+   const SphDerived& d = ctx->derived;
+   DevParams P;
+   memset(&P, 0, sizeof(P));
+   P.n = ctx->n_local;
+   P.n_owned = ctx->n_owned;
+   P.gx = p.grid_x; P.gy = p.grid_y; P.gz = p.grid_z;
+   P.fx = 2 * p.grid_x; P.fy = 2 * p.grid_y; P.fz = 2 * p.grid_z;
+   P.examine = p.examine_count;
+   P.use_gravity = p.use_uniform_gravity;
+   P.use_walls = p.use_wall_collision;
+   P.h = p.h; P.h2 = d.h2; P.h_times2 = d.h_times2; P.h_times2_inv = d.h_times2_inv;
+   P.hs = d.h_scaled; P.hs2 = d.h_scaled2;
+   P.k1 = d.kernel1; P.k2 = d.kernel2; P.k3 = d.kernel3;
+   P.scale = p.simulation_scale;
+   P.dt = p.time_step;
+   P.pos_dt = p.time_step * (1.0f / p.simulation_scale);   // sph.cpp:49, 956
+   P.rho0 = p.rho0; P.stiffness = p.stiffness; P.viscosity = p.viscosity; P.damping = p.damping;
+   P.cfl = p.cfl_limit; P.cfl2 = d.cfl_limit2;
+   P.neg_gm = -p.grav_constant * p.central_mass;
+   P.gm = p.grav_constant * p.central_mass;
+   P.cx = d.central_pos[0]; P.cy = d.central_pos[1]; P.cz = d.central_pos[2];
+   P.softening = d.softening;
+   P.gvx = p.gravity[0]; P.gvy = p.gravity[1]; P.gvz = p.gravity[2];
+   P.max_x = d.max_x; P.max_y = d.max_y; P.max_z = d.max_z;
+   P.z_lo = -std::numeric_limits<float>::infinity();
+   P.z_hi = std::numeric_limits<float>::infinity();
+   return P;
+}
+
+extern "C" {
+
+int sphb200_default_params(SphParams* p)
+{
+   if (!p)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null params");
+   memset(p, 0, sizeof(*p));
+   p->particle_count = 32 * 1024;          // M * 1024, M = 32 (sph.cpp:29-31, 59)
+   p->grid_x = p->grid_y = p->grid_z = 32; // sph.cpp:60-62
+   p->examine_count = 32;                  // sph.cpp:98
+   p->neighbor_mode = SPHB200_NEIGHBORS_REFERENCE_SAMPLED;
+   p->h = 0.1f;                            // sph.cpp:47
+   p->simulation_scale = 1.0f;             // sph.cpp:48
+   p->time_step = 0.001f;                  // sph.cpp:70
+   p->rho0 = 0.1f;                         // sph.cpp:74
+   p->stiffness = 0.001f;                  // sph.cpp:75
+   p->viscosity = 0.01f;                   // sph.cpp:77
+   p->damping = 0.001f;                    // sph.cpp:78
+   p->cfl_limit = 10000.0f;                // sph.cpp:89
+   p->grav_constant = 4.3009e-3f;          // sph.cpp:80
+   p->central_mass = 1e+5f;                // sph.cpp:81
+   p->central_pos[0] = p->central_pos[1] = p->central_pos[2] = -1.0f;   // box centre (sph.cpp:83-85)
+   p->softening = -1.0f;                   // h * scale (sph.cpp:86)
+   return SPHB200_OK;
+}
+
+int sphb200_derive(const SphParams* p, SphDerived* out)
+{
+   if (!p || !out)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null argument");
+   std::string why;
+   if (validate(*p, why))
+      return sph_fail(nullptr, SPHB200_E_INVALID, why);
+   derive(*p, *out);
+   return SPHB200_OK;
+}
+
+const char* sphb200_last_error(const sphb200_ctx* ctx)
+{
+   return ctx ? ctx->error.c_str() : g_error.c_str();
+}
+
+int sphb200_create(const SphParams* p, int device, sphb200_ctx** out)
+{
+   if (!p || !out)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null argument");
+   *out = nullptr;
+   std::string why;
+   if (validate(*p, why))
+      return sph_fail(nullptr, SPHB200_E_INVALID, why);
+   int ndev = 0;
+   cudaError_t e = cudaGetDeviceCount(&ndev);
+   if (e != cudaSuccess || ndev == 0)
+      return sph_fail(nullptr, SPHB200_E_CUDA,
+                      std::string("no CUDA device (this library has no CPU fallback): ") + cudaGetErrorString(e));
+   if (device < 0)
+   {
+      if (cudaGetDevice(&device) != cudaSuccess)
+         device = 0;
+   }
+   if (device >= ndev)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "device index out of range");
+   sphb200_ctx* ctx = new (std::nothrow) sphb200_ctx();
+   if (!ctx)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "out of host memory");
+   ctx->params = *p;
+   derive(*p, ctx->derived);
+   ctx->device = device;
+   ctx->capacity = p->particle_count;
+   ctx->n_local = p->particle_count;
+   ctx->n_owned = p->particle_count;
+   ctx->cells_voxel = p->grid_x * p->grid_y * p->grid_z;
+   ctx->cells_fine = 8 * ctx->cells_voxel;
+   ctx->cells_alloc = p->neighbor_mode == SPHB200_NEIGHBORS_FULL ? ctx->cells_fine : ctx->cells_voxel;
+   *out = ctx;   // from here on errors are reported on the context; caller destroys it
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(device));
+   SPH_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+   ctx->own_stream = true;
+   const size_t n = (size_t)ctx->capacity;
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->pos4, n));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->vel4, n));
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->pos4, 0, sizeof(float4) * (n ? n : 1), ctx->stream));
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->vel4, 0, sizeof(float4) * (n ? n : 1), ctx->stream));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->keys, n));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->keys_sorted, n));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->idx_iota, n));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->idx_sorted, n));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->cell_count, (size_t)ctx->cells_alloc + 1));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->cell_start, (size_t)ctx->cells_alloc + 1));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->s_posA4, n));   // also the upload / download staging
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->s_velB4, n));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->stage_f, n));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->nbr_count, n));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->rho, n));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->acc4, n));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->voxel_id, n));
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->rho, 0, sizeof(float) * (n ? n : 1), ctx->stream));
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->acc4, 0, sizeof(float4) * (n ? n : 1), ctx->stream));
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->nbr_count, 0, sizeof(int) * (n ? n : 1), ctx->stream));
+   int max_blocks = (int)((n + 127) / 128) + 1;
+   if (p->neighbor_mode == SPHB200_NEIGHBORS_FULL)
+   {
+      SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->s_pos4, n));
+      SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->s_rho, n));
+      SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->s_acc4, n));
+      SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->s_count, n));
+      int tiles = sph_full_tile_count(ctx);
+      if (tiles > max_blocks)
+         max_blocks = tiles;
+      int rc = sph_full_configure(ctx);
+      if (rc)
+         return rc;
+   }
+   else
+   {
+      int rc = alloc_lists(ctx);
+      if (rc)
+         return rc;
+   }
+   ctx->partial_blocks = max_blocks;
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->d_block_partials, 2 * (size_t)max_blocks));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->d_scalars, 1));
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(StepScalars), ctx->stream));
+   for (int i = 0; i < 8; i++)
+      SPH_CUDA_CHECK(ctx, cudaEventCreate(&ctx->ev[i]));
+   int rc = sph_grid_setup(ctx);
+   if (rc)
+      return rc;
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+   return SPHB200_OK;
+}
+
+int sphb200_destroy(sphb200_ctx* ctx)
+{
+   if (!ctx)
+      return SPHB200_OK;
+   cudaSetDevice(ctx->device);
+   if (ctx->stream)
+      cudaStreamSynchronize(ctx->stream);
+   sph_comm_free(ctx);
+   void* bufs[] = {ctx->pos4, ctx->vel4, ctx->gid, ctx->keys, ctx->keys_sorted, ctx->idx_iota, ctx->idx_sorted,
+                   ctx->cell_count, ctx->cell_start, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
+                   ctx->s_acc4, ctx->s_count, ctx->nbr_idx, ctx->nbr_dist, ctx->nbr_count, ctx->rho, ctx->acc4,
+                   ctx->voxel_id, ctx->vg_count, ctx->vg_start, ctx->vg_members, ctx->vg_keys, ctx->cub_temp,
+                   ctx->d_scalars, ctx->d_block_partials, ctx->stage_f};
+   for (void* b : bufs)
+      if (b)
+         cudaFree(b);
+   for (int i = 0; i < 8; i++)
+      if (ctx->ev[i])
+         cudaEventDestroy(ctx->ev[i]);
+   if (ctx->own_stream && ctx->stream)
+      cudaStreamDestroy(ctx->stream);
+   delete ctx;
+   return SPHB200_OK;
+}
+
+int sphb200_get_params(const sphb200_ctx* ctx, SphParams* out)
+{
+   if (!ctx || !out)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null argument");
+   *out = ctx->params;
+   return SPHB200_OK;
+}
+
+int sphb200_get_derived(const sphb200_ctx* ctx, SphDerived* out)
+{
+   if (!ctx || !out)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null argument");
+   *out = ctx->derived;
+   return SPHB200_OK;
+}
+
+// runtime scalars only -- the reference's setters (sph.cpp:1225-1289) plus the
+// constants a harness pokes through protected members.  Structural fields
+// (counts, grid, h, scale, mode) are fixed at create.
+int sphb200_set_params(sphb200_ctx* ctx, const SphParams* p)
+{
+   if (!ctx || !p)
+      return sph_fail(ctx, SPHB200_E_INVALID, "null argument");
+   const SphParams& c = ctx->params;
+   if (p->particle_count != c.particle_count || p->grid_x != c.grid_x || p->grid_y != c.grid_y ||
+       p->grid_z != c.grid_z || p->examine_count != c.examine_count || p->neighbor_mode != c.neighbor_mode ||
+       p->h != c.h || p->simulation_scale != c.simulation_scale)
+      return sph_fail(ctx, SPHB200_E_INVALID,
+                      "set_params: particle_count/grid/examine_count/neighbor_mode/h/scale are fixed at create");
+   ctx->params = *p;
+   derive(ctx->params, ctx->derived);
+   return SPHB200_OK;
+}
+
+int sphb200_set_stream(sphb200_ctx* ctx, void* cuda_stream)
+{
+   if (!ctx)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null context");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+   if (ctx->own_stream)
+      cudaStreamDestroy(ctx->stream);
+   if (cuda_stream)
+   {
+      ctx->stream = (cudaStream_t)cuda_stream;
+      ctx->own_stream = false;
+   }
+   else
+   {
+      SPH_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+   }
+   return SPHB200_OK;
+}
+
+int sphb200_upload_state(sphb200_ctx* ctx, const float* pos_xyz, const float* vel_xyz, const float* mass)
+{
+   if (!ctx || !pos_xyz || !vel_xyz)
+      return sph_fail(ctx, SPHB200_E_INVALID, "upload_state: null argument");
+   if (ctx->comm)
+      return sph_fail(ctx, SPHB200_E_INVALID, "upload_state: slab contexts use sphb200_upload_slab");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   const int n = ctx->capacity;
+   cudaStream_t st = ctx->stream;
+   if (n > 0)
+   {
+      float* d_pos = reinterpret_cast<float*>(ctx->s_posA4);
+      float* d_vel = reinterpret_cast<float*>(ctx->s_velB4);
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(d_pos, pos_xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(d_vel, vel_xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+      if (mass)
+         SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->stage_f, mass, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+      k_pack_state<<<blocks_for(n), kThreads, 0, st>>>(n, d_pos, d_vel, mass ? ctx->stage_f : nullptr, ctx->pos4,
+                                                       ctx->vel4);
+      ctx->launches++;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   }
+   ctx->n_local = ctx->n_owned = n;
+   ctx->lists_valid = false;
+   ctx->snapshot_valid = false;
+   ctx->voxel_ids_valid = false;
+   ctx->unsorted_valid = false;
+   ctx->stepped = false;
+   return SPHB200_OK;
+}
+
+int sphb200_step(sphb200_ctx* ctx, int n_steps)
+{
+   if (!ctx || n_steps < 0)
+      return sph_fail(ctx, SPHB200_E_INVALID, "step: bad argument");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   for (int s = 0; s < n_steps; s++)
+   {
+      int rc;
+      if (ctx->comm)
+      {
+         rc = sph_comm_exchange(ctx);
+         if (rc)
+            return rc;
+      }
+      rc = ctx->params.neighbor_mode == SPHB200_NEIGHBORS_FULL ? sph_step_full(ctx) : sph_step_sampled(ctx);
+      if (rc)
+         return rc;
+      ctx->stepped = true;
+   }
+   return SPHB200_OK;
+}
+
+int sphb200_synchronize(sphb200_ctx* ctx)
+{
+   if (!ctx)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null context");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+   return SPHB200_OK;
+}
+
+int sphb200_download(sphb200_ctx* ctx, int field, void* dst, size_t dst_bytes)
+{
+   if (!ctx || !dst)
+      return sph_fail(ctx, SPHB200_E_INVALID, "download: null argument");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   const int n = ctx->n_local;
+   const size_t E = (size_t)ctx->params.examine_count;
+   cudaStream_t st = ctx->stream;
+   const bool full = ctx->params.neighbor_mode == SPHB200_NEIGHBORS_FULL;
+   size_t need = 0;
+   const void* src = nullptr;
+   switch (field)
+   {
+   case SPHB200_F_POSITION:
+   case SPHB200_F_VELOCITY:
+   case SPHB200_F_ACCELERATION:
+   {
+      need = sizeof(float) * 3 * (size_t)n;
+      const float4* from = field == SPHB200_F_POSITION ? ctx->pos4 : field == SPHB200_F_VELOCITY ? ctx->vel4 : ctx->acc4;
+      if (field == SPHB200_F_ACCELERATION && full && !ctx->unsorted_valid)
+      {
+         int rc = sph_full_unsort(ctx);
+         if (rc)
+            return rc;
+      }
+      float* stage = reinterpret_cast<float*>(field == SPHB200_F_VELOCITY ? ctx->s_velB4 : ctx->s_posA4);
+      if (n > 0)
+      {
+         k_unpack_xyz<<<blocks_for(n), kThreads, 0, st>>>(n, from, stage);
+         ctx->launches++;
+         SPH_CUDA_CHECK(ctx, cudaGetLastError());
+      }
+      src = stage;
+      break;
+   }
+   case SPHB200_F_MASS:
+      need = sizeof(float) * (size_t)n;
+      if (n > 0)
+      {
+         k_unpack_w<<<blocks_for(n), kThreads, 0, st>>>(n, ctx->pos4, ctx->stage_f);
+         ctx->launches++;
+         SPH_CUDA_CHECK(ctx, cudaGetLastError());
+      }
+      src = ctx->stage_f;
+      break;
+   case SPHB200_F_DENSITY:
+   case SPHB200_F_NEIGHBOR_COUNT:
+      if (full && !ctx->unsorted_valid)
+      {
+         int rc = sph_full_unsort(ctx);
+         if (rc)
+            return rc;
+      }
+      need = (field == SPHB200_F_DENSITY ? sizeof(float) : sizeof(int)) * (size_t)n;
+      src = field == SPHB200_F_DENSITY ? (const void*)ctx->rho : (const void*)ctx->nbr_count;
+      break;
+   case SPHB200_F_VOXEL_ID:
+   {
+      int rc = sph_refresh_voxel_ids(ctx);
+      if (rc)
+         return rc;
+      need = sizeof(int) * (size_t)n;
+      src = ctx->voxel_id;
+      break;
+   }
+   case SPHB200_F_VOXEL_COORD:
+   {
+      // mVoxelCoords (sph.h:144): decoded on the host from the voxel ids
+      need = sizeof(int) * 3 * (size_t)n;
+      if (dst_bytes < need)
+         return sph_fail(ctx, SPHB200_E_INVALID, "download: destination too small");
+      int rc = sph_refresh_voxel_ids(ctx);
+      if (rc)
+         return rc;
+      int* out = static_cast<int*>(dst);
+      int* ids = out + 2 * (size_t)n;   // tail of the destination as scratch
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(ids, ctx->voxel_id, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, st));
+      SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+      const int gx = ctx->params.grid_x, gy = ctx->params.grid_y;
+      for (int i = 0; i < n; i++)
+      {
+         int id = ids[i];
+         out[3 * (size_t)i] = id % gx;
+         out[3 * (size_t)i + 1] = (id / gx) % gy;
+         out[3 * (size_t)i + 2] = id / (gx * gy);
+      }
+      return SPHB200_OK;
+   }
+   case SPHB200_F_GRID_START:
+   case SPHB200_F_GRID_MEMBERS:
+   case SPHB200_F_CELL_COUNT:
+      return sph_download_grid(ctx, field, dst, dst_bytes);
+   case SPHB200_F_NEIGHBOR_INDEX:
+   case SPHB200_F_NEIGHBOR_DISTANCE:
+      if (!ctx->lists_valid)
+         return sph_fail(ctx, SPHB200_E_INVALID,
+                         full ? "download: call sphb200_build_neighbor_lists after a FULL-mode step first"
+                              : "download: no step has produced neighbour lists yet");
+      need = sizeof(uint32_t) * (size_t)n * E;
+      src = field == SPHB200_F_NEIGHBOR_INDEX ? (const void*)ctx->nbr_idx : (const void*)ctx->nbr_dist;
+      break;
+   case SPHB200_F_FINE_KEY:
+      if (!full || !ctx->snapshot_valid)
+         return sph_fail(ctx, SPHB200_E_INVALID, "download: fine keys exist after a FULL-mode step only");
+      need = sizeof(int) * (size_t)n;
+      src = ctx->keys;
+      break;
+   default:
+      return sph_fail(ctx, SPHB200_E_INVALID, "download: unknown field");
+   }
+   if (dst_bytes < need)
+      return sph_fail(ctx, SPHB200_E_INVALID, "download: destination too small");
+   if (need)
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, st));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+   return SPHB200_OK;
+}
+
+int sphb200_step_host(sphb200_ctx* ctx, float* pos_xyz, float* vel_xyz, const float* mass)
+{
+   int rc = sphb200_upload_state(ctx, pos_xyz, vel_xyz, mass);
+   if (rc)
+      return rc;
+   rc = sphb200_step(ctx, 1);
+   if (rc)
+      return rc;
+   const int n = ctx->n_local;
+   cudaStream_t st = ctx->stream;
+   if (n > 0)
+   {
+      float* d_pos = reinterpret_cast<float*>(ctx->s_posA4);
+      float* d_vel = reinterpret_cast<float*>(ctx->s_velB4);
+      k_unpack_xyz<<<blocks_for(n), kThreads, 0, st>>>(n, ctx->pos4, d_pos);
+      k_unpack_xyz<<<blocks_for(n), kThreads, 0, st>>>(n, ctx->vel4, d_vel);
+      ctx->launches += 2;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(pos_xyz, d_pos, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, st));
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(vel_xyz, d_vel, sizeof(float) * 3 * (size_t)n, cudaMemcpyDeviceToHost, st));
+   }
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+   return SPHB200_OK;
+}
+
+int sphb200_build_neighbor_lists(sphb200_ctx* ctx)
+{
+   if (!ctx)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null context");
+   if (ctx->params.neighbor_mode != SPHB200_NEIGHBORS_FULL)
+      return ctx->lists_valid ? SPHB200_OK
+                              : sph_fail(ctx, SPHB200_E_INVALID, "build_neighbor_lists: step first");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   int rc = alloc_lists(ctx);
+   if (rc)
+      return rc;
+   return sph_full_build_lists(ctx);
+}
+
+int sphb200_get_energies(sphb200_ctx* ctx, float* e_kin, float* e_pot)
+{
+   if (!ctx || !e_kin || !e_pot)
+      return sph_fail(ctx, SPHB200_E_INVALID, "null argument");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   int rc = fetch_scalars(ctx);
+   if (rc)
+      return rc;
+   *e_kin = (float)ctx->h_scalars.e_kin;
+   *e_pot = (float)ctx->h_scalars.e_pot;
+   return SPHB200_OK;
+}
+
+int sphb200_get_neighbor_stats(sphb200_ctx* ctx, long long* total, int* max_count, int* min_count)
+{
+   if (!ctx)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null context");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   int rc = fetch_scalars(ctx);
+   if (rc)
+      return rc;
+   if (total) *total = (long long)ctx->h_scalars.nbr_total;
+   if (max_count) *max_count = ctx->h_scalars.nbr_max;
+   if (min_count) *min_count = ctx->h_scalars.nbr_min;
+   return SPHB200_OK;
+}
+
+int sphb200_get_timings(sphb200_ctx* ctx, float ms[6])
+{
+   if (!ctx || !ms)
+      return sph_fail(ctx, SPHB200_E_INVALID, "null argument");
+   for (int i = 0; i < 6; i++)
+      ms[i] = 0.0f;
+   if (!ctx->params.enable_timers || !ctx->stepped)
+      return SPHB200_OK;
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+   for (int i = 0; i < 6; i++)
+   {
+      float t = 0.0f;
+      if (cudaEventElapsedTime(&t, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess)
+         ms[i] = t;
+      else
+         cudaGetLastError();
+   }
+   return SPHB200_OK;
+}
+
+int sphb200_get_launch_count(const sphb200_ctx* ctx, long long* launches)
+{
+   if (!ctx || !launches)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null argument");
+   *launches = ctx->launches;
+   return SPHB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,845 @@
+// sph_full.cu -- FULL neighbour policy: the throughput path.
+//
+// Two fused sweeps over particles in fine-cell order (cell edge h, 27-cell
+// neighbourhood == the reference's 2x2x2 voxel octant, sph.cpp:504-556):
+//   density sweep : poly6 density (computeDensity, sph.cpp:721-766) + the
+//                   equation of state folded into two per-particle force
+//                   coefficients (sph.cpp:785, 829-834) + velocity gather
+//   force sweep   : spiky pressure + viscosity (computeAcceleration,
+//                   sph.cpp:778-934) + integrate (937-1022) + wall collision
+//                   (1025-1148) + energy / neighbour statistics
+// No neighbour list is ever stored.  A CTA owns a 4x4x4 block of fine cells,
+// stages the block plus its one-cell halo (36 x-contiguous row segments of the
+// cell-sorted arrays) in shared memory, and each thread walks the 9 x-runs of
+// its particle there.  The force sweep separates the cheap distance test from
+// the expensive pair body through a per-thread ring of hit indices so that a
+// warp only executes pair bodies for real neighbours, in ascending cell order
+// (the order the in-loop viscosity scaling of sph.cpp:880-882 depends on).
+// Blocks too dense for shared memory are split (4x4x2, 4x2x2, 2x2x2) and, past
+// that, processed straight from global memory (same arithmetic).
+#include "sph_math.cuh"
+
+namespace
+{
+
+constexpr int TB = 4;                       // tile edge in fine cells
+constexpr int HROWS = (TB + 2) * (TB + 2);  // halo rows (y,z) of a full tile
+constexpr int CSW = TB + 3;                 // cell_start entries per halo row
+constexpr int TROWS = TB * TB;              // target rows of a full tile
+constexpr int kTileThreads = 256;
+constexpr int kCapDensity = 2560;           // staged particles, density sweep (16 B each)
+constexpr int kCapForce = 2400;             // staged particles, force sweep (32 B each)
+constexpr int QCAP = 64;                    // hit ring entries per thread (power of two)
+constexpr int kFlatThreads = 128;
+
+struct TileLayout
+{
+   int row_g0[HROWS];        // first global (sorted) index of the halo row segment
+   int row_delta[HROWS];     // smem index = global index + row_delta (0 when not staged)
+   int row_len[HROWS];
+   int cs[HROWS][CSW];       // cell_start of cells x0-1 .. x0+bx and the end, per halo row
+   int tgt_off[TROWS + 1];   // prefix of target counts per target row
+   int total;                // staged particles
+   int ntargets;
+};
+
+// ---- pair arithmetic ---------------------------------------------------------
+
+// poly6 term of one candidate, branch-free: t = max(hs2 - d2*scale^2, 0);
+// sum += m_j * t^3  (K1 is applied once at the end).  Candidates outside h add 0.
+__device__ __forceinline__ float density_term(float sum, float xi, float yi, float zi, float4 pj, float hs2,
+                                              float scale2)
+{
+   float dx = xi - pj.x, dy = yi - pj.y, dz = zi - pj.z;
+   float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+   float t = fmaxf(fmaf(-d2, scale2, hs2), 0.0f);
+   return fmaf(pj.w * t, t * t, sum);
+}
+
+struct ForceI     // per-target constants of computeAcceleration (sph.cpp:785-798)
+{
+   float x, y, z, vx, vy, vz;
+   float pi_div;   // p_i * rhoiInv^2
+   float s;        // mu * rhoiInv   (in-loop viscosity scale, sph.cpp:880-882)
+};
+
+// one neighbour of computeAcceleration's loop (sph.cpp:825-884).  pj = (x,y,z,fA),
+// vj = (vx,vy,vz,fB) with fA, fB from sph_force_coeffs.  d2 is the exact squared
+// distance that passed the d2 < h2 test.
+__device__ __forceinline__ void force_pair(const DevParams& P, const ForceI& I, float4 pj, float4 vj, float d2,
+                                           Vec3& pg, Vec3& vt)
+{
+   float d = sqrtf(d2) * P.scale;
+   float inv = __fdividef(P.k2, d + 0.01f);
+   float hd = P.hs - d;
+   float c = (hd * hd) * (I.pi_div * pj.w) * inv;
+   pg.x = fmaf((I.x - pj.x) * P.scale, c, pg.x);
+   pg.y = fmaf((I.y - pj.y) * P.scale, c, pg.y);
+   pg.z = fmaf((I.z - pj.z) * P.scale, c, pg.z);
+   float cv = hd * vj.w;
+   vt.x = fmaf(vj.x - I.vx, cv, vt.x) * I.s;
+   vt.y = fmaf(vj.y - I.vy, cv, vt.y) * I.s;
+   vt.z = fmaf(vj.z - I.vz, cv, vt.z) * I.s;
+}
+
+__device__ __forceinline__ ForceI make_force_i(const DevParams& P, float4 pi, float4 vi, float rho)
+{
+   ForceI I;
+   I.x = pi.x; I.y = pi.y; I.z = pi.z;
+   I.vx = vi.x; I.vy = vi.y; I.vz = vi.z;
+   float p = (rho - P.rho0) * P.stiffness;
+   float rinv = (p > 0.0f) ? __fdiv_rn(1.0f, p) : 1.0f;   // 1/p_i, not 1/rho_i (sph.cpp:786)
+   I.pi_div = p * (rinv * rinv);
+   I.s = P.viscosity * rinv;
+   return I;
+}
+
+// density sweep epilogue for sorted particle k
+__device__ __forceinline__ void density_store(const DevParams& P, int k, float4 pi, float sum,
+                                              const uint32_t* __restrict__ idx_sorted,
+                                              const float4* __restrict__ vel4, float4* __restrict__ s_posA4,
+                                              float4* __restrict__ s_velB4, float* __restrict__ s_rho)
+{
+   // the particle itself sat in the centre run at d2 = 0: remove its own term
+   // (the reference skips realIndex == particleIndex, sph.cpp:737)
+   float self = __fmul_rn(pi.w * P.hs2, P.hs2 * P.hs2);
+   float rho = P.k1 * (sum - self);
+   float fA, fB;
+   sph_force_coeffs(P, rho, pi.w, fA, fB);
+   float4 v = __ldg(&vel4[idx_sorted[k]]);
+   s_rho[k] = rho;
+   s_posA4[k] = make_float4(pi.x, pi.y, pi.z, fA);
+   s_velB4[k] = make_float4(v.x, v.y, v.z, fB);
+}
+
+// force sweep epilogue: tail of computeAcceleration, integrate, walls, write-back
+__device__ __forceinline__ void force_store(const DevParams& P, int k, const ForceI& I, Vec3 vt, Vec3 pg, int count,
+                                            const float4* __restrict__ s_pos4,
+                                            const uint32_t* __restrict__ idx_sorted, float4* __restrict__ pos4,
+                                            float4* __restrict__ vel4, float4* __restrict__ s_acc4,
+                                            int* __restrict__ s_count, double& ek, double& ep)
+{
+   Vec3 a = sph_finish_acceleration(P, vt, pg, I.x, I.y, I.z);
+   float mass = s_pos4[k].w;
+   float r[3] = {I.x, I.y, I.z};
+   float v[3] = {I.vx, I.vy, I.vz};
+   float e_kin, e_pot;
+   sph_integrate(P, r, v, a, mass, e_kin, e_pot);
+   uint32_t o = idx_sorted[k];
+   pos4[o] = make_float4(r[0], r[1], r[2], mass);
+   vel4[o] = make_float4(v[0], v[1], v[2], 0.0f);
+   s_acc4[k] = make_float4(a.x, a.y, a.z, 0.0f);
+   s_count[k] = count;
+   ek = e_kin;
+   ep = e_pot;
+}
+
+// the 9 x-runs of sorted particle k straight from the global cell table
+__device__ __forceinline__ void global_runs(const DevParams& P, uint32_t key, const uint32_t* __restrict__ cell_start,
+                                            int b[9], int e[9])
+{
+   int cx = (int)(key % (uint32_t)P.fx);
+   int t = (int)(key / (uint32_t)P.fx);
+   int cy = t % P.fy, cz = t / P.fy;
+   int x0 = max(cx - 1, 0), x1 = min(cx + 1, P.fx - 1);
+#pragma unroll
+   for (int dz = 0; dz < 3; dz++)
+#pragma unroll
+      for (int dy = 0; dy < 3; dy++)
+      {
+         int z = cz + dz - 1, y = cy + dy - 1;
+         int r = dz * 3 + dy;
+         if (z < 0 || z >= P.fz || y < 0 || y >= P.fy)
+         {
+            b[r] = 0;
+            e[r] = 0;
+         }
+         else
+         {
+            int row = (z * P.fy + y) * P.fx;
+            b[r] = (int)cell_start[row + x0];
+            e[r] = (int)cell_start[row + x1 + 1];
+         }
+      }
+}
+
+// ---- untiled kernels (kernel_variant = 1; also the arithmetic of the dense
+//      fallback): one thread per sorted particle, candidates through L1/L2 -----
+
+__global__ void __launch_bounds__(kFlatThreads)
+   k_density_flat(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ keys_sorted,
+                  const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ idx_sorted,
+                  const float4* __restrict__ vel4, float4* __restrict__ s_posA4, float4* __restrict__ s_velB4,
+                  float* __restrict__ s_rho)
+{
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k >= P.n)
+      return;
+   float4 pi = s_pos4[k];
+   int b[9], e[9];
+   global_runs(P, keys_sorted[k], cell_start, b, e);
+   float scale2 = P.scale * P.scale;
+   float sum = 0.0f;
+#pragma unroll
+   for (int r = 0; r < 9; r++)
+      for (int j = b[r]; j < e[r]; j++)
+         sum = density_term(sum, pi.x, pi.y, pi.z, __ldg(&s_pos4[j]), P.hs2, scale2);
+   density_store(P, k, pi, sum, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
+}
+
+__global__ void __launch_bounds__(kFlatThreads)
+   k_force_flat(DevParams P, const float4* __restrict__ s_pos4, const float4* __restrict__ s_posA4,
+                const float4* __restrict__ s_velB4, const float* __restrict__ s_rho,
+                const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ cell_start,
+                const uint32_t* __restrict__ idx_sorted, float4* __restrict__ pos4, float4* __restrict__ vel4,
+                float4* __restrict__ s_acc4, int* __restrict__ s_count, double* __restrict__ block_partials,
+                StepScalars* scal)
+{
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   double ek = 0.0, ep = 0.0;
+   unsigned long long cnt = 0;
+   int cmax = -1, cmin = 0x7fffffff;
+   if (k < P.n)
+   {
+      ForceI I = make_force_i(P, s_posA4[k], s_velB4[k], s_rho[k]);
+      int b[9], e[9];
+      global_runs(P, keys_sorted[k], cell_start, b, e);
+      Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
+      int count = 0;
+#pragma unroll
+      for (int r = 0; r < 9; r++)
+         for (int j = b[r]; j < e[r]; j++)
+         {
+            float4 pj = __ldg(&s_posA4[j]);
+            float d2 = sph_dist2_exact(I.x, I.y, I.z, pj.x, pj.y, pj.z);
+            if (d2 < P.h2 && j != k)
+            {
+               force_pair(P, I, pj, __ldg(&s_velB4[j]), d2, pg, vt);
+               count++;
+            }
+         }
+      force_store(P, k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, ek, ep);
+      cnt = (unsigned long long)count;
+      cmax = count;
+      cmin = count;
+   }
+   sph_block_reduce_scalars(ek, ep, cnt, cmax, cmin, block_partials, scal);
+}
+
+// ---- tiled kernels -----------------------------------------------------------
+
+struct SubTile
+{
+   int x0, y0, z0;      // origin in fine cells
+   int bx, by, bz;      // extent in fine cells
+};
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+   return __reduce_add_sync(0xffffffffu, v);
+}
+
+// number of particles in the sub-tile plus its one-cell halo (warp-cooperative)
+__device__ int halo_population(const DevParams& P, const SubTile& t, const uint32_t* __restrict__ cell_start)
+{
+   int lane = threadIdx.x & 31;
+   int rows = (t.by + 2) * (t.bz + 2);
+   int sum = 0;
+   for (int hr = lane; hr < rows; hr += 32)
+   {
+      int y = t.y0 - 1 + hr % (t.by + 2);
+      int z = t.z0 - 1 + hr / (t.by + 2);
+      if (y >= 0 && y < P.fy && z >= 0 && z < P.fz)
+      {
+         int row = (z * P.fy + y) * P.fx;
+         int xa = max(t.x0 - 1, 0), xb = min(t.x0 + t.bx + 1, P.fx);
+         sum += (int)cell_start[row + xb] - (int)cell_start[row + xa];
+      }
+   }
+   return warp_sum(sum);
+}
+
+// fills the layout for one sub-tile.  Called by all threads; ends with a barrier.
+// staged = true lays the halo rows out back to back in shared memory.
+__device__ void setup_layout(const DevParams& P, const SubTile& t, const uint32_t* __restrict__ cell_start,
+                             bool staged, TileLayout& L)
+{
+   const int rows = (t.by + 2) * (t.bz + 2);
+   const int csw = t.bx + 3;
+   for (int i = threadIdx.x; i < rows * csw; i += blockDim.x)
+   {
+      int hr = i / csw, c = i % csw;
+      int y = t.y0 - 1 + hr % (t.by + 2);
+      int z = t.z0 - 1 + hr / (t.by + 2);
+      int v = 0;
+      if (y >= 0 && y < P.fy && z >= 0 && z < P.fz)
+      {
+         int x = min(max(t.x0 - 1 + c, 0), P.fx);   // x == fx addresses the end of the row
+         v = (int)cell_start[(z * P.fy + y) * P.fx + x];
+      }
+      L.cs[hr][c] = v;
+   }
+   __syncthreads();
+   if (threadIdx.x < 32)
+   {
+      // row lengths and their exclusive prefix (rows <= 36: two lanes-wide passes)
+      int lane = threadIdx.x;
+      int carry = 0;
+      for (int base = 0; base < rows; base += 32)
+      {
+         int hr = base + lane;
+         int len = 0, g0 = 0;
+         if (hr < rows)
+         {
+            g0 = L.cs[hr][0];
+            len = L.cs[hr][csw - 1] - g0;
+         }
+         int incl = len;
+#pragma unroll
+         for (int o = 1; o < 32; o <<= 1)
+         {
+            int up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+               incl += up;
+         }
+         if (hr < rows)
+         {
+            L.row_g0[hr] = g0;
+            L.row_len[hr] = len;
+            L.row_delta[hr] = staged ? (carry + incl - len) - g0 : 0;
+         }
+         carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0)
+         L.total = carry;
+      // targets per target row (by*bz <= 16 rows)
+      int trows = t.by * t.bz;
+      int tc = 0;
+      if (lane < trows)
+      {
+         int hr = (lane / t.by + 1) * (t.by + 2) + (lane % t.by + 1);
+         tc = L.cs[hr][t.bx + 1] - L.cs[hr][1];
+      }
+      int incl = tc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+         int up = __shfl_up_sync(0xffffffffu, incl, o);
+         if (lane >= o)
+            incl += up;
+      }
+      if (lane < trows)
+         L.tgt_off[lane] = incl - tc;
+      if (lane == 31)
+      {
+         L.tgt_off[trows] = incl;
+         L.ntargets = incl;
+      }
+   }
+   __syncthreads();
+}
+
+// copies the halo rows of `src` (global, cell-sorted) into shared memory
+__device__ __forceinline__ void stage_rows(const SubTile& t, const TileLayout& L, const float4* __restrict__ src,
+                                           float4* __restrict__ dst)
+{
+   const int rows = (t.by + 2) * (t.bz + 2);
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+   for (int hr = warp; hr < rows; hr += nwarps)
+   {
+      int g0 = L.row_g0[hr], len = L.row_len[hr], off = g0 + L.row_delta[hr];
+      for (int j = lane; j < len; j += 32)
+         dst[off + j] = __ldg(&src[g0 + j]);
+   }
+}
+
+struct Target
+{
+   int k;        // global sorted index
+   int hr0;      // halo row of the target's own cell row
+   int lx;       // cell column inside the halo row table (1..bx)
+};
+
+// maps flat target number -> particle and its cell (all from the smem tables)
+__device__ __forceinline__ Target locate_target(const SubTile& t, const TileLayout& L, int tnum)
+{
+   int trows = t.by * t.bz;
+   int r = 0;
+#pragma unroll 4
+   for (int i = 1; i < trows; i++)
+      r += (tnum >= L.tgt_off[i]) ? 1 : 0;
+   Target T;
+   T.hr0 = (r / t.by + 1) * (t.by + 2) + (r % t.by + 1);
+   T.k = L.cs[T.hr0][1] + (tnum - L.tgt_off[r]);
+   int lx = 1;
+   for (int i = 2; i <= t.bx; i++)
+      lx += (T.k >= L.cs[T.hr0][i]) ? 1 : 0;
+   T.lx = lx;
+   return T;
+}
+
+// picks the sub-division level of this CTA's tile: 0 = 4x4x4 ... 3 = 2x2x2,
+// 4 = nothing fits (process from global memory).  Evaluated by warp 0.
+__device__ int choose_level(const DevParams& P, int X0, int Y0, int Z0, const uint32_t* __restrict__ cell_start,
+                            int cap)
+{
+   for (int level = 0; level < 4; level++)
+   {
+      int bz = level >= 1 ? TB / 2 : TB;
+      int by = level >= 2 ? TB / 2 : TB;
+      int bx = level >= 3 ? TB / 2 : TB;
+      bool fits = true;
+      for (int z = 0; z < TB && fits; z += bz)
+         for (int y = 0; y < TB && fits; y += by)
+            for (int x = 0; x < TB && fits; x += bx)
+            {
+               SubTile t = {X0 + x, Y0 + y, Z0 + z, bx, by, bz};
+               fits = halo_population(P, t, cell_start) <= cap;
+            }
+      if (fits)
+         return level;
+   }
+   return 4;
+}
+
+__device__ __forceinline__ void tile_origin(const DevParams& P, int& X0, int& Y0, int& Z0)
+{
+   int tx = (P.fx + TB - 1) / TB, ty = (P.fy + TB - 1) / TB;
+   int b = blockIdx.x;
+   X0 = (b % tx) * TB;
+   Y0 = ((b / tx) % ty) * TB;
+   Z0 = (b / (tx * ty)) * TB;
+}
+
+// particles of the un-haloed tile (quick exit for empty space); warp 0
+__device__ int tile_population(const DevParams& P, int X0, int Y0, int Z0, const uint32_t* __restrict__ cell_start)
+{
+   int lane = threadIdx.x & 31;
+   int sum = 0;
+   if (lane < TROWS)
+   {
+      int y = Y0 + lane % TB, z = Z0 + lane / TB;
+      if (y < P.fy && z < P.fz)
+      {
+         int row = (z * P.fy + y) * P.fx;
+         sum = (int)cell_start[row + min(X0 + TB, P.fx)] - (int)cell_start[row + X0];
+      }
+   }
+   return warp_sum(sum);
+}
+
+template <bool STAGED>
+__device__ __forceinline__ void density_targets(const DevParams& P, const SubTile& t, const TileLayout& L,
+                                                const float4* __restrict__ src,
+                                                const uint32_t* __restrict__ idx_sorted,
+                                                const float4* __restrict__ vel4, float4* __restrict__ s_posA4,
+                                                float4* __restrict__ s_velB4, float* __restrict__ s_rho)
+{
+   const float scale2 = P.scale * P.scale;
+   for (int tnum = threadIdx.x; tnum < L.ntargets; tnum += blockDim.x)
+   {
+      Target T = locate_target(t, L, tnum);
+      float4 pi = src[T.k + L.row_delta[T.hr0]];
+      float sum = 0.0f;
+#pragma unroll
+      for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+         for (int dy = -1; dy <= 1; dy++)
+         {
+            int hr = T.hr0 + dz * (t.by + 2) + dy;
+            int delta = L.row_delta[hr];
+            int b = L.cs[hr][T.lx - 1] + delta;
+            int e = L.cs[hr][T.lx + 2] + delta;
+#pragma unroll 4
+            for (int j = b; j < e; j++)
+            {
+               float4 pj = STAGED ? src[j] : __ldg(&src[j]);
+               sum = density_term(sum, pi.x, pi.y, pi.z, pj, P.hs2, scale2);
+            }
+         }
+      density_store(P, T.k, pi, sum, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
+   }
+}
+
+__global__ void __launch_bounds__(kTileThreads)
+   k_density_tiled(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ cell_start,
+                   const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ vel4,
+                   float4* __restrict__ s_posA4, float4* __restrict__ s_velB4, float* __restrict__ s_rho)
+{
+   extern __shared__ __align__(16) unsigned char smem_raw[];
+   float4* sp = reinterpret_cast<float4*>(smem_raw);
+   __shared__ TileLayout L;
+   __shared__ int s_level, s_pop;
+   int X0, Y0, Z0;
+   tile_origin(P, X0, Y0, Z0);
+   if (threadIdx.x < 32)
+   {
+      int pop = tile_population(P, X0, Y0, Z0, cell_start);
+      int level = pop > 0 ? choose_level(P, X0, Y0, Z0, cell_start, kCapDensity) : 0;
+      if (threadIdx.x == 0)
+      {
+         s_pop = pop;
+         s_level = level;
+      }
+   }
+   __syncthreads();
+   if (s_pop == 0)
+      return;
+   const int level = s_level;
+   const int bz = (level >= 1 && level < 4) ? TB / 2 : TB;
+   const int by = (level >= 2 && level < 4) ? TB / 2 : TB;
+   const int bx = (level >= 3 && level < 4) ? TB / 2 : TB;
+   for (int z = 0; z < TB; z += bz)
+      for (int y = 0; y < TB; y += by)
+         for (int x = 0; x < TB; x += bx)
+         {
+            SubTile t = {X0 + x, Y0 + y, Z0 + z, bx, by, bz};
+            setup_layout(P, t, cell_start, level < 4, L);
+            if (L.ntargets > 0)
+            {
+               if (level < 4)
+               {
+                  stage_rows(t, L, s_pos4, sp);
+                  __syncthreads();
+                  density_targets<true>(P, t, L, sp, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
+               }
+               else
+                  density_targets<false>(P, t, L, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
+            }
+            __syncthreads();   // smem and layout are reused by the next sub-tile
+         }
+}
+
+// drains up to `n` queued hits of this lane (n is warp-uniform)
+__device__ __forceinline__ void drain_hits(const DevParams& P, const ForceI& I, const float4* __restrict__ spA,
+                                           const float4* __restrict__ svB, const unsigned short* __restrict__ q,
+                                           int& qh, int qt, int n, Vec3& pg, Vec3& vt)
+{
+   for (int it = 0; it < n; it++)
+   {
+      if (qh < qt)
+      {
+         int j = q[(qh & (QCAP - 1)) * kTileThreads];
+         qh++;
+         float4 pj = spA[j];
+         float d2 = sph_dist2_exact(I.x, I.y, I.z, pj.x, pj.y, pj.z);
+         force_pair(P, I, pj, svB[j], d2, pg, vt);
+      }
+   }
+}
+
+__global__ void __launch_bounds__(kTileThreads)
+   k_force_tiled(DevParams P, const float4* __restrict__ s_pos4, const float4* __restrict__ s_posA4,
+                 const float4* __restrict__ s_velB4, const float* __restrict__ s_rho,
+                 const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ idx_sorted,
+                 float4* __restrict__ pos4, float4* __restrict__ vel4, float4* __restrict__ s_acc4,
+                 int* __restrict__ s_count, double* __restrict__ block_partials, StepScalars* scal)
+{
+   extern __shared__ __align__(16) unsigned char smem_raw[];
+   float4* spA = reinterpret_cast<float4*>(smem_raw);
+   float4* svB = spA + kCapForce;
+   unsigned short* queue = reinterpret_cast<unsigned short*>(svB + kCapForce);
+   __shared__ TileLayout L;
+   __shared__ int s_level, s_pop;
+   int X0, Y0, Z0;
+   tile_origin(P, X0, Y0, Z0);
+   if (threadIdx.x < 32)
+   {
+      int pop = tile_population(P, X0, Y0, Z0, cell_start);
+      int level = pop > 0 ? choose_level(P, X0, Y0, Z0, cell_start, kCapForce) : 0;
+      if (threadIdx.x == 0)
+      {
+         s_pop = pop;
+         s_level = level;
+      }
+   }
+   __syncthreads();
+   if (s_pop == 0)
+      return;   // block_partials were zeroed by the host for this step
+   double ek = 0.0, ep = 0.0;
+   unsigned long long cnt = 0;
+   int cmax = -1, cmin = 0x7fffffff;
+   const int level = s_level;
+   const int bz = (level >= 1 && level < 4) ? TB / 2 : TB;
+   const int by = (level >= 2 && level < 4) ? TB / 2 : TB;
+   const int bx = (level >= 3 && level < 4) ? TB / 2 : TB;
+   const unsigned short* q = queue + threadIdx.x;
+   unsigned short* qw = queue + threadIdx.x;
+   for (int z = 0; z < TB; z += bz)
+      for (int y = 0; y < TB; y += by)
+         for (int x = 0; x < TB; x += bx)
+         {
+            SubTile t = {X0 + x, Y0 + y, Z0 + z, bx, by, bz};
+            setup_layout(P, t, cell_start, level < 4, L);
+            if (L.ntargets > 0 && level < 4)
+            {
+               stage_rows(t, L, s_posA4, spA);
+               stage_rows(t, L, s_velB4, svB);
+               __syncthreads();
+               // all lanes of a warp run the same number of outer iterations so
+               // that the warp-wide reductions below are convergent
+               int rounds = (L.ntargets + blockDim.x - 1) / blockDim.x;
+               for (int round = 0; round < rounds; round++)
+               {
+                  int tnum = round * blockDim.x + threadIdx.x;
+                  bool active = tnum < L.ntargets;
+                  Target T = locate_target(t, L, active ? tnum : 0);
+                  int self = T.k + L.row_delta[T.hr0];
+                  ForceI I = make_force_i(P, spA[self], svB[self], s_rho[T.k]);
+                  Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
+                  int qh = 0, qt = 0;
+#pragma unroll
+                  for (int dz = -1; dz <= 1; dz++)
+#pragma unroll
+                     for (int dy = -1; dy <= 1; dy++)
+                     {
+                        int hr = T.hr0 + dz * (t.by + 2) + dy;
+                        int delta = L.row_delta[hr];
+                        int b = L.cs[hr][T.lx - 1] + delta;
+                        int e = active ? L.cs[hr][T.lx + 2] + delta : b;
+                        int chunks = __reduce_max_sync(0xffffffffu, (e - b + 31) >> 5);
+                        for (int c = 0; c < chunks; c++)
+                        {
+                           // make room for 32 more hits in every lane's ring
+                           int need = __reduce_max_sync(0xffffffffu, (qt - qh) + 32 - QCAP);
+                           if (need > 0)
+                              drain_hits(P, I, spA, svB, q, qh, qt, need, pg, vt);
+                           int j0 = b + c * 32;
+                           int j1 = min(j0 + 32, e);
+#pragma unroll 4
+                           for (int j = j0; j < j1; j++)
+                           {
+                              float4 pj = spA[j];
+                              float d2 = sph_dist2_exact(I.x, I.y, I.z, pj.x, pj.y, pj.z);
+                              if (d2 < P.h2 && j != self)
+                              {
+                                 qw[(qt & (QCAP - 1)) * kTileThreads] = (unsigned short)j;
+                                 qt++;
+                              }
+                           }
+                        }
+                     }
+                  int rest = __reduce_max_sync(0xffffffffu, qt - qh);
+                  drain_hits(P, I, spA, svB, q, qh, qt, rest, pg, vt);
+                  if (active)
+                  {
+                     double e1, e2;
+                     force_store(P, T.k, I, vt, pg, qt, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, e1, e2);
+                     ek += e1;
+                     ep += e2;
+                     cnt += (unsigned long long)qt;
+                     cmax = max(cmax, qt);
+                     cmin = min(cmin, qt);
+                  }
+               }
+            }
+            else if (L.ntargets > 0)
+            {
+               // too dense to stage: same arithmetic straight from global memory
+               for (int tnum = threadIdx.x; tnum < L.ntargets; tnum += blockDim.x)
+               {
+                  Target T = locate_target(t, L, tnum);
+                  ForceI I = make_force_i(P, s_posA4[T.k], s_velB4[T.k], s_rho[T.k]);
+                  Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
+                  int count = 0;
+                  for (int dz = -1; dz <= 1; dz++)
+                     for (int dy = -1; dy <= 1; dy++)
+                     {
+                        int hr = T.hr0 + dz * (t.by + 2) + dy;
+                        int b = L.cs[hr][T.lx - 1], e = L.cs[hr][T.lx + 2];
+                        for (int j = b; j < e; j++)
+                        {
+                           float4 pj = __ldg(&s_posA4[j]);
+                           float d2 = sph_dist2_exact(I.x, I.y, I.z, pj.x, pj.y, pj.z);
+                           if (d2 < P.h2 && j != T.k)
+                           {
+                              force_pair(P, I, pj, __ldg(&s_velB4[j]), d2, pg, vt);
+                              count++;
+                           }
+                        }
+                     }
+                  double e1, e2;
+                  force_store(P, T.k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, e1, e2);
+                  ek += e1;
+                  ep += e2;
+                  cnt += (unsigned long long)count;
+                  cmax = max(cmax, count);
+                  cmin = min(cmin, count);
+               }
+            }
+            __syncthreads();
+         }
+   sph_block_reduce_scalars(ek, ep, cnt, cmax, cmin, block_partials, scal);
+}
+
+// ---- on-demand outputs --------------------------------------------------------
+
+// mNeighbors / mNeighborDistancesScaled of the last step (sph.h:173-174) in the
+// order the force sweep visited them: ascending (fine cell, particle index).
+__global__ void __launch_bounds__(kFlatThreads)
+   k_build_lists(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ keys_sorted,
+                 const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ idx_sorted,
+                 uint32_t* __restrict__ nbr_idx, float* __restrict__ nbr_dist, int* __restrict__ nbr_count,
+                 StepScalars* scal)
+{
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k >= P.n)
+      return;
+   float4 pi = s_pos4[k];
+   int b[9], e[9];
+   global_runs(P, keys_sorted[k], cell_start, b, e);
+   const int E = P.examine;
+   uint32_t o = idx_sorted[k];
+   int count = 0;
+#pragma unroll
+   for (int r = 0; r < 9; r++)
+      for (int j = b[r]; j < e[r]; j++)
+      {
+         float4 pj = __ldg(&s_pos4[j]);
+         float d2 = sph_dist2_exact(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
+         if (d2 < P.h2 && j != k)
+         {
+            if (count < E)
+            {
+               nbr_idx[(size_t)o * E + count] = idx_sorted[j];
+               nbr_dist[(size_t)o * E + count] = __fmul_rn(__fsqrt_rn(d2), P.scale);
+            }
+            count++;
+         }
+      }
+   nbr_count[o] = count;
+   if (count > E)
+      atomicMax(&scal->overflow, count);
+}
+
+// sorted per-particle outputs back to particle-index order (download only)
+__global__ void __launch_bounds__(kFlatThreads)
+   k_unsort(int n, const uint32_t* __restrict__ idx_sorted, const float* __restrict__ s_rho,
+            const float4* __restrict__ s_acc4, const int* __restrict__ s_count, float* __restrict__ rho,
+            float4* __restrict__ acc4, int* __restrict__ nbr_count)
+{
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k >= n)
+      return;
+   uint32_t o = idx_sorted[k];
+   rho[o] = s_rho[k];
+   acc4[o] = s_acc4[k];
+   nbr_count[o] = s_count[k];
+}
+
+size_t density_smem() { return sizeof(float4) * (size_t)kCapDensity; }
+size_t force_smem() { return sizeof(float4) * 2 * (size_t)kCapForce + sizeof(unsigned short) * QCAP * kTileThreads; }
+
+}  // namespace
+
+int sph_full_configure(sphb200_ctx* ctx)
+{
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)density_smem()));
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_force_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)force_smem()));
+   return SPHB200_OK;
+}
+
+int sph_full_tile_count(const sphb200_ctx* ctx)
+{
+   int fx = 2 * ctx->params.grid_x, fy = 2 * ctx->params.grid_y, fz = 2 * ctx->params.grid_z;
+   return ((fx + TB - 1) / TB) * ((fy + TB - 1) / TB) * ((fz + TB - 1) / TB);
+}
+
+int sph_step_full(sphb200_ctx* ctx)
+{
+   DevParams P = sph_dev_params(ctx);
+   const int n = ctx->n_local;
+   cudaStream_t st = ctx->stream;
+   const bool timed = ctx->params.enable_timers != 0;
+   if (timed) cudaEventRecord(ctx->ev[0], st);
+   int rc = sph_bin_and_sort(ctx, true);
+   if (rc)
+      return rc;
+   if (timed) cudaEventRecord(ctx->ev[1], st);
+   rc = sph_reset_scalars(ctx);
+   if (rc)
+      return rc;
+   if (timed) cudaEventRecord(ctx->ev[2], st);   // neighbour search is fused into the two sweeps
+   if (n == 0)
+      return SPHB200_OK;
+   const bool tiled = ctx->params.kernel_variant != 1;
+   int blocks;
+   if (tiled)
+   {
+      blocks = sph_full_tile_count(ctx);
+      SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_block_partials, 0, sizeof(double) * 2 * (size_t)blocks, st));
+      k_density_tiled<<<blocks, kTileThreads, density_smem(), st>>>(P, ctx->s_pos4, ctx->cell_start,
+                                                                   ctx->idx_sorted, ctx->vel4, ctx->s_posA4,
+                                                                   ctx->s_velB4, ctx->s_rho);
+      if (timed) cudaEventRecord(ctx->ev[3], st);
+      if (timed) cudaEventRecord(ctx->ev[4], st);
+      k_force_tiled<<<blocks, kTileThreads, force_smem(), st>>>(P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4,
+                                                               ctx->s_rho, ctx->cell_start, ctx->idx_sorted,
+                                                               ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count,
+                                                               ctx->d_block_partials, ctx->d_scalars);
+   }
+   else
+   {
+      blocks = (n + kFlatThreads - 1) / kFlatThreads;
+      k_density_flat<<<blocks, kFlatThreads, 0, st>>>(P, ctx->s_pos4, ctx->keys_sorted, ctx->cell_start,
+                                                      ctx->idx_sorted, ctx->vel4, ctx->s_posA4, ctx->s_velB4,
+                                                      ctx->s_rho);
+      if (timed) cudaEventRecord(ctx->ev[3], st);
+      if (timed) cudaEventRecord(ctx->ev[4], st);
+      k_force_flat<<<blocks, kFlatThreads, 0, st>>>(P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
+                                                    ctx->keys_sorted, ctx->cell_start, ctx->idx_sorted, ctx->pos4,
+                                                    ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
+                                                    ctx->d_scalars);
+   }
+   ctx->launches += 2;
+   SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   if (timed) cudaEventRecord(ctx->ev[5], st);   // integrate is fused into the force sweep
+   rc = sph_finish_scalars(ctx, blocks);
+   if (rc)
+      return rc;
+   if (timed) cudaEventRecord(ctx->ev[6], st);
+   ctx->lists_valid = false;
+   ctx->snapshot_valid = true;
+   ctx->unsorted_valid = false;
+   return SPHB200_OK;
+}
+
+int sph_full_unsort(sphb200_ctx* ctx)
+{
+   const int n = ctx->n_local;
+   if (n == 0 || !ctx->snapshot_valid)
+      return SPHB200_OK;
+   k_unsort<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, ctx->stream>>>(
+      n, ctx->idx_sorted, ctx->s_rho, ctx->s_acc4, ctx->s_count, ctx->rho, ctx->acc4, ctx->nbr_count);
+   ctx->launches++;
+   SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   ctx->unsorted_valid = true;
+   return SPHB200_OK;
+}
+
+int sph_full_build_lists(sphb200_ctx* ctx)
+{
+   if (!ctx->snapshot_valid)
+      return sph_fail(ctx, SPHB200_E_INVALID, "build_neighbor_lists: no FULL-mode step snapshot (step first)");
+   DevParams P = sph_dev_params(ctx);
+   const int n = ctx->n_local;
+   if (n > 0)
+   {
+      k_build_lists<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, ctx->stream>>>(
+         P, ctx->s_pos4, ctx->keys_sorted, ctx->cell_start, ctx->idx_sorted, ctx->nbr_idx, ctx->nbr_dist,
+         ctx->nbr_count, ctx->d_scalars);
+      ctx->launches++;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   }
+   StepScalars h;
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(&h, ctx->d_scalars, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+   if (h.overflow > ctx->params.examine_count)
+      return sph_fail(ctx, SPHB200_E_CAPACITY,
+                      "build_neighbor_lists: a particle has " + std::to_string(h.overflow) +
+                         " neighbours, examine_count is " + std::to_string(ctx->params.examine_count));
+   ctx->lists_valid = true;
+   return SPHB200_OK;
+}

@@ -1,0 +1,291 @@
+// sph_grid.cu -- voxel binning, device radix sort, cell tables, cell-order gather.
+//
+// Replaces clearGrid + voxelizeParticles (sph.cpp:429-481): instead of
+// QList::push_back per particle, particles get a cell key, are stably sorted by
+// it FROM ORIGINAL-INDEX ORDER every step (so the order inside a cell is
+// ascending particle index == the reference's push_back order, sph.cpp:476-480)
+// and an exclusive-scan table cell_start[c] .. cell_start[c+1] replaces the lists.
+#include <cub/cub.cuh>
+
+#include "sph_math.cuh"
+
+namespace
+{
+
+constexpr int kThreads = 256;
+
+// SAMPLED mode: key = voxel id (sph.cpp:443-473, 1151-1154).
+// FULL mode:    key = fine-cell id, fine = 2*voxel + (orientation > h) per axis
+//               (the octant rule of sph.cpp:504-515), x fastest.
+template <bool FINE>
+__global__ void __launch_bounds__(kThreads) k_cell_keys(DevParams P, const float4* __restrict__ pos4,
+                                                         uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ cell_count,
+                                                         int* __restrict__ voxel_id_out)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= P.n)
+      return;
+   float4 p = pos4[i];
+   int vx = sph_voxel_coord(p.x, P.h_times2_inv, P.gx);
+   int vy = sph_voxel_coord(p.y, P.h_times2_inv, P.gy);
+   int vz = sph_voxel_coord(p.z, P.h_times2_inv, P.gz);
+   uint32_t key;
+   if (FINE)
+   {
+      int cx = 2 * vx + sph_upper_half(p.x, vx, P.h_times2, P.h);
+      int cy = 2 * vy + sph_upper_half(p.y, vy, P.h_times2, P.h);
+      int cz = 2 * vz + sph_upper_half(p.z, vz, P.h_times2, P.h);
+      key = (uint32_t)((cz * P.fy + cy) * P.fx + cx);
+   }
+   else
+      key = (uint32_t)sph_voxel_id(vx, vy, vz, P.gx, P.gy);
+   keys[i] = key;
+   if (voxel_id_out)
+      voxel_id_out[i] = sph_voxel_id(vx, vy, vz, P.gx, P.gy);
+   atomicAdd(&cell_count[key], 1u);
+}
+
+__global__ void __launch_bounds__(kThreads) k_iota(uint32_t* a, int n)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n)
+      a[i] = (uint32_t)i;
+}
+
+// particles into cell order: one 16-byte gather per particle
+__global__ void __launch_bounds__(kThreads) k_gather_pos(int n, const uint32_t* __restrict__ idx_sorted,
+                                                          const float4* __restrict__ pos4,
+                                                          float4* __restrict__ s_pos4)
+{
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k < n)
+      s_pos4[k] = __ldg(&pos4[idx_sorted[k]]);
+}
+
+__global__ void k_reset_scalars(StepScalars* s)
+{
+   s->e_kin = 0.0;
+   s->e_pot = 0.0;
+   s->nbr_total = 0ull;
+   s->nbr_max = -1;
+   s->nbr_min = 0x7fffffff;
+   s->overflow = 0;
+}
+
+// second stage of the deterministic energy reduction: one block, fixed order
+__global__ void __launch_bounds__(1024) k_finish_scalars(const double* __restrict__ partials, int blocks,
+                                                         StepScalars* s)
+{
+   __shared__ double sk[1024], sp[1024];
+   double ek = 0.0, ep = 0.0;
+   for (int b = threadIdx.x; b < blocks; b += 1024)
+   {
+      ek += partials[2 * b];
+      ep += partials[2 * b + 1];
+   }
+   sk[threadIdx.x] = ek;
+   sp[threadIdx.x] = ep;
+   __syncthreads();
+   for (int o = 512; o > 0; o >>= 1)
+   {
+      if (threadIdx.x < o)
+      {
+         sk[threadIdx.x] += sk[threadIdx.x + o];
+         sp[threadIdx.x] += sp[threadIdx.x + o];
+      }
+      __syncthreads();
+   }
+   if (threadIdx.x == 0)
+   {
+      s->e_kin = sk[0];
+      s->e_pot = sp[0];
+   }
+}
+
+int blocks_for(int n) { return (n + kThreads - 1) / kThreads; }
+
+}  // namespace
+
+int sph_reset_scalars(sphb200_ctx* ctx)
+{
+   k_reset_scalars<<<1, 1, 0, ctx->stream>>>(ctx->d_scalars);
+   ctx->launches++;
+   SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   return SPHB200_OK;
+}
+
+int sph_finish_scalars(sphb200_ctx* ctx, int blocks)
+{
+   k_finish_scalars<<<1, 1024, 0, ctx->stream>>>(ctx->d_block_partials, blocks, ctx->d_scalars);
+   ctx->launches++;
+   SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   return SPHB200_OK;
+}
+
+// keys -> histogram -> exclusive scan -> stable radix sort of (key, index) ->
+// (FULL) gather positions into cell order.
+int sph_bin_and_sort(sphb200_ctx* ctx, bool fine)
+{
+   DevParams P = sph_dev_params(ctx);
+   const int n = ctx->n_local;
+   const int cells = fine ? ctx->cells_fine : ctx->cells_voxel;
+   cudaStream_t st = ctx->stream;
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->cell_count, 0, sizeof(uint32_t) * ((size_t)cells + 1), st));
+   if (n > 0)
+   {
+      if (fine)
+         k_cell_keys<true><<<blocks_for(n), kThreads, 0, st>>>(P, ctx->pos4, ctx->keys, ctx->cell_count,
+                                                               ctx->voxel_id);
+      else
+         k_cell_keys<false><<<blocks_for(n), kThreads, 0, st>>>(P, ctx->pos4, ctx->keys, ctx->cell_count,
+                                                                ctx->voxel_id);
+      ctx->launches++;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+      ctx->voxel_ids_valid = true;
+   }
+   size_t temp = ctx->cub_temp_bytes;
+   SPH_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_temp, temp, ctx->cell_count, ctx->cell_start,
+                                                     cells + 1, st));
+   ctx->launches += 2;
+   if (n > 0)
+   {
+      int bits = 1;
+      while (bits < 32 && (1ll << bits) < (long long)cells)
+         bits++;
+      temp = ctx->cub_temp_bytes;
+      SPH_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp, temp, ctx->keys, ctx->keys_sorted,
+                                                          ctx->idx_iota, ctx->idx_sorted, n, 0, bits, st));
+      ctx->launches += 1 + 2 * ((bits + 7) / 8);
+      if (fine)
+      {
+         k_gather_pos<<<blocks_for(n), kThreads, 0, st>>>(n, ctx->idx_sorted, ctx->pos4, ctx->s_pos4);
+         ctx->launches++;
+         SPH_CUDA_CHECK(ctx, cudaGetLastError());
+      }
+   }
+   return SPHB200_OK;
+}
+
+// scratch sizing + iota; called once from sphb200_create
+int sph_grid_setup(sphb200_ctx* ctx)
+{
+   size_t t_scan = 0, t_sort = 0;
+   cub::DeviceScan::ExclusiveSum(nullptr, t_scan, (uint32_t*)nullptr, (uint32_t*)nullptr, ctx->cells_alloc + 1);
+   cub::DeviceRadixSort::SortPairs(nullptr, t_sort, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
+                                   (uint32_t*)nullptr, ctx->capacity > 0 ? ctx->capacity : 1, 0, 32);
+   ctx->cub_temp_bytes = (t_scan > t_sort ? t_scan : t_sort) + 256;
+   SPH_CUDA_CHECK(ctx, cudaMalloc(&ctx->cub_temp, ctx->cub_temp_bytes));
+   if (ctx->capacity > 0)
+   {
+      k_iota<<<blocks_for(ctx->capacity), kThreads, 0, ctx->stream>>>(ctx->idx_iota, ctx->capacity);
+      ctx->launches++;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   }
+   return SPHB200_OK;
+}
+
+// ---- on-demand views of the voxel grid for the reference-facing getters -----
+// SPH::mVoxelIds / mGrid (sph.h:142-146, 172) as of the LAST binning (the
+// reference's members also hold the pre-integration binning after step()).
+// voxel ids are written by every step; the per-voxel membership lists are only
+// rebuilt here when a caller asks -- the GL view's drawVoxels needs just
+// mGrid[c].count() (visualization.cpp:188-193).
+namespace
+{
+__global__ void __launch_bounds__(kThreads) k_voxel_ids(DevParams P, const float4* __restrict__ pos4,
+                                                         int* __restrict__ voxel_id)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= P.n)
+      return;
+   float4 p = pos4[i];
+   voxel_id[i] = sph_voxel_id(sph_voxel_coord(p.x, P.h_times2_inv, P.gx), sph_voxel_coord(p.y, P.h_times2_inv, P.gy),
+                              sph_voxel_coord(p.z, P.h_times2_inv, P.gz), P.gx, P.gy);
+}
+
+__global__ void __launch_bounds__(kThreads) k_histogram(int n, const int* __restrict__ keys,
+                                                         uint32_t* __restrict__ count)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i < n)
+      atomicAdd(&count[keys[i]], 1u);
+}
+}  // namespace
+
+int sph_refresh_voxel_ids(sphb200_ctx* ctx)
+{
+   if (ctx->voxel_ids_valid || ctx->n_local == 0)
+      return SPHB200_OK;
+   DevParams P = sph_dev_params(ctx);
+   k_voxel_ids<<<blocks_for(ctx->n_local), kThreads, 0, ctx->stream>>>(P, ctx->pos4, ctx->voxel_id);
+   ctx->launches++;
+   SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   ctx->voxel_ids_valid = true;
+   return SPHB200_OK;
+}
+
+int sph_download_grid(sphb200_ctx* ctx, int field, void* dst, size_t bytes)
+{
+   const int n = ctx->n_local;
+   const int cells = ctx->cells_voxel;
+   cudaStream_t st = ctx->stream;
+   int rc = sph_refresh_voxel_ids(ctx);
+   if (rc)
+      return rc;
+   if (!ctx->vg_count)
+   {
+      SPH_CUDA_CHECK(ctx, cudaMalloc(&ctx->vg_count, sizeof(uint32_t) * ((size_t)cells + 1)));
+      SPH_CUDA_CHECK(ctx, cudaMalloc(&ctx->vg_start, sizeof(uint32_t) * ((size_t)cells + 1)));
+      SPH_CUDA_CHECK(ctx, cudaMalloc(&ctx->vg_members, sizeof(uint32_t) * (size_t)(ctx->capacity + 1)));
+      SPH_CUDA_CHECK(ctx, cudaMalloc(&ctx->vg_keys, sizeof(uint32_t) * (size_t)(ctx->capacity + 1)));
+   }
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->vg_count, 0, sizeof(uint32_t) * ((size_t)cells + 1), st));
+   if (n > 0)
+   {
+      k_histogram<<<blocks_for(n), kThreads, 0, st>>>(n, ctx->voxel_id, ctx->vg_count);
+      ctx->launches++;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   }
+   size_t need = 0;
+   const void* src = nullptr;
+   if (field == SPHB200_F_CELL_COUNT)
+   {
+      need = sizeof(int) * (size_t)cells;
+      src = ctx->vg_count;
+   }
+   else
+   {
+      size_t temp = ctx->cub_temp_bytes;
+      SPH_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_temp, temp, ctx->vg_count, ctx->vg_start,
+                                                        cells + 1, st));
+      ctx->launches += 2;
+      if (field == SPHB200_F_GRID_START)
+      {
+         need = sizeof(int) * ((size_t)cells + 1);
+         src = ctx->vg_start;
+      }
+      else if (field == SPHB200_F_GRID_MEMBERS)
+      {
+         int bits = 1;
+         while (bits < 32 && (1ll << bits) < (long long)cells)
+            bits++;
+         temp = ctx->cub_temp_bytes;
+         if (n > 0)
+            SPH_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp, temp, (const uint32_t*)ctx->voxel_id,
+                                                                ctx->vg_keys, ctx->idx_iota, ctx->vg_members, n, 0,
+                                                                bits, st));
+         ctx->launches += 1 + 2 * ((bits + 7) / 8);
+         need = sizeof(uint32_t) * (size_t)n;
+         src = ctx->vg_members;
+      }
+      else
+         return sph_fail(ctx, SPHB200_E_INVALID, "sph_download_grid: bad field");
+   }
+   if (bytes < need)
+      return sph_fail(ctx, SPHB200_E_INVALID, "download: destination too small");
+   if (need)
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, src, need, cudaMemcpyDeviceToHost, st));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+   return SPHB200_OK;
+}

@@ -1,0 +1,140 @@
+// sph_internal.h -- context and device-parameter block shared by the .cu files.
+#ifndef SPHB200_INTERNAL_H
+#define SPHB200_INTERNAL_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "sphb200.h"
+
+// Everything a kernel needs, passed by value (fits the 4 KB parameter space).
+// Derived constants are computed on the host with the reference constructor's
+// own expressions (sph.cpp:47-95) so that they carry the same rounding.
+struct DevParams
+{
+   int n;                 // particles on this device (owned + ghosts in slab mode)
+   int n_owned;           // particles that are integrated / written back
+   int gx, gy, gz;        // voxel grid (edge 2h)
+   int fx, fy, fz;        // fine grid (edge h) = 2 * voxel grid
+   int examine;           // E
+   int use_gravity, use_walls;
+   float h, h2, h_times2, h_times2_inv;
+   float hs, hs2;         // h * scale, (h*scale)^2
+   float k1, k2, k3;      // poly6, spiky-gradient, viscosity-laplacian coefficients
+   float scale;           // mSimulationScale
+   float dt, pos_dt;      // mTimeStep, mTimeStep * (1/scale)  (sph.cpp:956)
+   float rho0, stiffness, viscosity, damping;
+   float cfl, cfl2;
+   float neg_gm;          // (-G) * M   (sph.cpp:913, 987)
+   float gm;              // G * M      (sph.cpp:1007)
+   float cx, cy, cz;      // central mass position
+   float softening;
+   float gvx, gvy, gvz;   // uniform gravity
+   float max_x, max_y, max_z;
+   float z_lo, z_hi;      // slab mode: owned z range in world units (else -inf/+inf)
+};
+
+struct StepScalars     // per-step reductions, one device struct
+{
+   double e_kin, e_pot;
+   unsigned long long nbr_total;
+   int nbr_max, nbr_min;
+   int overflow;        // FULL list builder: count above capacity seen
+};
+
+struct SlabComm;       // sph_comm.cu
+
+struct sphb200_ctx
+{
+   SphParams params;
+   SphDerived derived;
+   int device;
+   cudaStream_t stream;
+   bool own_stream;
+   std::string error;
+   long long launches;
+
+   int capacity;          // allocated particle slots
+   int n_local;           // particles currently on this device (== capacity single GPU)
+   int n_owned;
+   int cells_voxel, cells_fine, cells_alloc;
+
+   // persistent state, original (upload) order: xyz+mass, vel+pad
+   float4* pos4;
+   float4* vel4;
+   uint32_t* gid;         // global ids (slab mode), else NULL
+
+   // per-step scratch
+   uint32_t *keys, *keys_sorted, *idx_iota, *idx_sorted;
+   uint32_t* cell_count;  // histogram, cells_alloc + 1
+   uint32_t* cell_start;  // exclusive scan, cells_alloc + 1
+   float4* s_pos4;        // sorted snapshot (x,y,z,m)
+   float4* s_posA4;       // sorted (x,y,z,fA)   force-pass record
+   float4* s_velB4;       // sorted (vx,vy,vz,fB)
+   float* s_rho;          // sorted density
+   float4* s_acc4;        // sorted acceleration (x,y,z,unused)
+   int* s_count;          // sorted neighbour count
+
+   // SAMPLED mode / on-demand lists, original order
+   uint32_t* nbr_idx;     // N * E
+   float* nbr_dist;       // N * E
+   int* nbr_count;        // N
+   float* rho;            // N  (original order)
+   float4* acc4;          // N  (original order)
+   int* voxel_id;         // N  (original order)
+   bool lists_valid;
+   bool voxel_ids_valid;  // voxel_id[] matches the last binning / current upload
+   bool snapshot_valid;   // sorted snapshot + cell table of the last FULL step present
+   uint32_t *vg_count, *vg_start, *vg_members, *vg_keys;   // lazily allocated voxel-grid views
+
+   void* cub_temp;
+   size_t cub_temp_bytes;
+   int key_bits;
+
+   StepScalars* d_scalars;
+   StepScalars h_scalars;
+   double* d_block_partials;   // per-block (ekin, epot) partials
+   int partial_blocks;
+
+   float* stage_f;             // N floats: mass staging for upload / download
+   bool unsorted_valid;        // rho / acc4 / nbr_count hold the last FULL step, particle order
+
+   cudaEvent_t ev[8];
+   float phase_ms[6];
+   bool stepped;
+
+   SlabComm* comm;
+};
+
+#define SPH_CUDA_CHECK(ctx, expr)                                                        \
+   do                                                                                    \
+   {                                                                                     \
+      cudaError_t _e = (expr);                                                           \
+      if (_e != cudaSuccess)                                                             \
+         return sph_fail(ctx, SPHB200_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+   } while (0)
+
+int sph_fail(sphb200_ctx* ctx, int code, const std::string& msg);
+DevParams sph_dev_params(const sphb200_ctx* ctx);
+
+// sph_grid.cu
+int sph_bin_and_sort(sphb200_ctx* ctx, bool fine);
+int sph_download_grid(sphb200_ctx* ctx, int field, void* dst, size_t bytes);
+int sph_refresh_voxel_ids(sphb200_ctx* ctx);
+int sph_grid_setup(sphb200_ctx* ctx);
+// sph_sampled.cu
+int sph_step_sampled(sphb200_ctx* ctx);
+// sph_full.cu
+int sph_step_full(sphb200_ctx* ctx);
+int sph_full_build_lists(sphb200_ctx* ctx);
+int sph_full_configure(sphb200_ctx* ctx);
+// sph_reduce.cu (in sph_grid.cu)
+int sph_reset_scalars(sphb200_ctx* ctx);
+int sph_finish_scalars(sphb200_ctx* ctx, int blocks);
+// sph_comm.cu
+int sph_comm_exchange(sphb200_ctx* ctx);
+void sph_comm_free(sphb200_ctx* ctx);
+
+#endif

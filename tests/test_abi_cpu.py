@@ -1,0 +1,72 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every
+symbol include/sphb200.h declares, derives the constructor constants like the
+reference, generates the reference's scenes, and fails loudly without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import smoothed_particle_hydrodynamics_b200 as S
+from smoothed_particle_hydrodynamics_b200 import binding
+from oracle import scenes
+from oracle.port import OracleSPH
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "sphb200.h")).read()
+    declared = set(re.findall(r"\b(sphb200_[a-z0-9_]+)\s*\(", header))
+    bound = {name for name, _, _ in binding.API}
+    assert declared == bound, declared ^ bound
+    L = S.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+
+
+def test_default_params_are_the_reference_constructor_literals():
+    p = S.default_params()
+    assert (p.particle_count, p.grid_x, p.grid_y, p.grid_z, p.examine_count) == (32768, 32, 32, 32, 32)
+    d = S.derive(p)
+    o = OracleSPH(init_scene=False)    # oracle_derive restates sph.cpp:47-95
+    for a, b in [(d.h2, o.p.h2), (d.h_times2_inv, o.p.h_times2_inv), (d.kernel1, o.p.kernel1),
+                 (d.kernel2, o.p.kernel2), (d.kernel3, o.p.kernel3), (d.max_x, o.p.max_x),
+                 (d.softening, o.p.softening), (d.cfl_limit2, o.p.cfl_limit2), (d.h_scaled9, o.p.hs9)]:
+        assert np.float32(a) == np.float32(b)
+    assert list(d.central_pos) == list(o.p.central_pos)
+    assert d.total_steps == 1000 and d.grid_cell_count == 32768
+
+
+def test_sphere_scene_is_the_reference_constructor_scene(golden_default):
+    pos, vel = S.scene_sphere(S.default_params())
+    assert np.array_equal(pos, golden_default["pos0"])
+    assert np.array_equal(vel, golden_default["vel0"])
+
+
+def test_lattice_scene_matches_numpy_restatement():
+    d = scenes.lattice_spacing(0.1, 40)
+    a = S.scene_lattice(32, 16, 32, d, origin=(0.2, 3.2, 0.6))
+    b = scenes.lattice_scene(32, 16, 32, d, origin=(0.2, 3.2, 0.6))
+    assert np.array_equal(a, b)
+    # any id range can be generated independently (slab ranks make their own particles)
+    c = S.scene_lattice(32, 16, 32, d, origin=(0.2, 3.2, 0.6), first_id=5000, count=777)
+    assert np.array_equal(c, b[5000:5777])
+    with pytest.raises(S.SphError):
+        S.scene_lattice(4, 4, 4, d, first_id=60, count=10)
+
+
+def test_invalid_params_are_rejected():
+    for kw in (dict(examine_count=4), dict(h=0.0), dict(grid=(0, 4, 4)), dict(neighbor_mode=7),
+               dict(grid=(2048, 2048, 2048))):
+        with pytest.raises(S.SphError):
+            S.derive(S.default_params(**kw))
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(S.SphError) as e:
+        S.SPH()
+    assert "no CUDA device" in str(e.value) and e.value.code == -2

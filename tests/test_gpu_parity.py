@@ -1,0 +1,308 @@
+"""GPU parity: the CUDA path (through the C ABI, libsphb200.so) against the CPU
+oracle (oracle/sph_oracle.c, pinned to the reference by tests/test_oracle.py)
+and against the committed golden fixtures (outputs of the reference itself).
+
+Bars:
+  * integer outputs -- voxel ids, cell membership, neighbour counts, ORDERED
+    neighbour lists (sampled mode) / neighbour sets (full mode): bit exact;
+  * density:      |d rho| / (|rho| + m W(0)) <= 1e-5
+  * acceleration: |d a|_inf / |a|_2 <= 1e-4, and >= 99.9 % of particles <= 1e-5
+  * new position / velocity: <= 1e-5 relative to max(|value|, field scale)
+"""
+import numpy as np
+import pytest
+
+from conftest import sparse_lists
+from oracle import scenes
+from oracle.port import FULL as O_FULL
+from oracle.port import SAMPLED as O_SAMPLED
+from oracle.port import OracleSPH
+
+pytestmark = pytest.mark.gpu
+
+S = pytest.importorskip("smoothed_particle_hydrodynamics_b200")
+F = S.Field
+
+RHO_TOL = 1e-5
+ACC_TOL_MAX = 1e-4
+ACC_TOL_BULK = 1e-5
+STATE_TOL = 1e-5
+
+
+def check_density(rho, ref, w0, tag=""):
+    err = np.abs(rho - ref) / (np.abs(ref) + w0)
+    assert np.nanmax(err) <= RHO_TOL, "%s density err %g" % (tag, np.nanmax(err))
+    assert np.array_equal(np.isnan(rho), np.isnan(ref))
+
+
+def check_acc(acc, ref, tag=""):
+    finite = np.isfinite(ref).all(axis=1)
+    assert np.array_equal(np.isfinite(acc).all(axis=1), finite), "%s non-finite rows differ" % tag
+    a, r = acc[finite].astype(np.float64), ref[finite].astype(np.float64)
+    norm = np.linalg.norm(r, axis=1)
+    err = np.abs(a - r).max(axis=1) / np.maximum(norm, 1e-30)
+    assert err.max() <= ACC_TOL_MAX, "%s acc err max %g" % (tag, err.max())
+    assert (err <= ACC_TOL_BULK).mean() >= 0.999, "%s acc bulk %g" % (tag, (err <= ACC_TOL_BULK).mean())
+
+
+def check_state(x, ref, scale, tag=""):
+    finite = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(x), finite), "%s non-finite entries differ" % tag
+    err = np.abs(x[finite].astype(np.float64) - ref[finite]) / np.maximum(np.abs(ref[finite]), scale)
+    assert err.max() <= STATE_TOL, "%s state err %g" % (tag, err.max())
+
+
+def w0_of(d, mass=1.0):
+    return mass * d.kernel1 * d.h_scaled6   # W(0) = K1 h^6
+
+
+# ---------------------------------------------------------------- sampled mode
+def test_sampled_default_scene_vs_reference_golden(golden_default):
+    g = golden_default
+    sph = S.SPH()     # reference constructor: defaults + seeded sphere
+    assert np.array_equal(sph.download(F.POSITION), g["pos0"])
+    assert np.array_equal(sph.download(F.VELOCITY), g["vel0"])
+    d = sph.derived
+    for s in (1, 2):
+        sph.step()
+        assert np.array_equal(sph.download(F.VOXEL_ID), g["voxel_ids_%d" % s])
+        assert np.array_equal(sph.download(F.GRID_MEMBERS), g["grid_members_%d" % s])
+        cnt = sph.download(F.NEIGHBOR_COUNT)
+        assert np.array_equal(cnt, g["nbr_count_%d" % s])
+        nb, nd = sparse_lists(sph.download(F.NEIGHBOR_INDEX), sph.download(F.NEIGHBOR_DISTANCE), cnt)
+        assert np.array_equal(nb, g["nbr_idx_%d" % s])        # ordered, bit exact
+        assert np.array_equal(nd, g["nbr_dist_%d" % s])       # IEEE sqrt: bit exact
+        ek, ep = sph.energies()
+        assert abs(ek - g["energy_%d" % s][0]) <= 1e-5 * abs(ek)
+        assert abs(ep - g["energy_%d" % s][1]) <= 1e-5 * abs(ep)
+        total, mx, mn = sph.neighbor_stats()
+        assert total == int(cnt.sum()) and mx == cnt.max() and mn == cnt.min()
+        if s == 1:
+            assert np.array_equal(sph.download(F.GRID_START), g["grid_start_1"])
+            check_density(sph.download(F.DENSITY), g["density_1"], w0_of(d), "default")
+            check_acc(sph.download(F.ACCELERATION), g["acc_1"], "default")
+            check_state(sph.download(F.POSITION), g["pos_1"], 1.0, "pos")
+            check_state(sph.download(F.VELOCITY), g["vel_1"], 1.0, "vel")
+    sph.close()
+
+
+def test_sampled_dense_random_state_vs_oracle():
+    rng = np.random.default_rng(7)
+    n = 32768
+    pos = (rng.random((n, 3)) * 1.6 + 2.4).astype(np.float32)
+    pos[:50] = -0.3                 # out of the box: clamped into edge voxels
+    pos[50:100] = 7.0
+    vel = rng.normal(0, 5, (n, 3)).astype(np.float32)
+    mass = (rng.random(n) + 0.5).astype(np.float32)
+    o = OracleSPH(init_scene=False)
+    o.set_state(pos, vel, mass)
+    sph = S.SPH(S.default_params(), init_scene=False)
+    sph.upload(pos, vel, mass)
+    d = sph.derived
+    for s in range(3):
+        o.step(O_SAMPLED)
+        sph.step_n(1)
+        assert np.array_equal(sph.download(F.VOXEL_ID), o.voxel_ids)
+        assert np.array_equal(sph.download(F.VOXEL_COORD), o.voxel_xyz)
+        assert np.array_equal(sph.download(F.GRID_START), o.start)
+        assert np.array_equal(sph.download(F.GRID_MEMBERS), o.members)
+        assert np.array_equal(sph.download(F.CELL_COUNT), np.diff(o.start))
+        cnt = sph.download(F.NEIGHBOR_COUNT)
+        assert np.array_equal(cnt, o.count) and cnt.max() > 8
+        nb, nd = sparse_lists(sph.download(F.NEIGHBOR_INDEX), sph.download(F.NEIGHBOR_DISTANCE), cnt)
+        onb, ond = sparse_lists(o.nbr, o.dist, o.count)
+        assert np.array_equal(nb, onb) and np.array_equal(nd, ond)
+        check_density(sph.download(F.DENSITY), o.rho, w0_of(d, mass), "dense s%d" % s)
+        check_acc(sph.download(F.ACCELERATION), o.acc, "dense s%d" % s)
+        check_state(sph.download(F.POSITION), o.pos, 1.0)
+        check_state(sph.download(F.VELOCITY), o.vel, 1.0)
+        # keep the two trajectories identical for the next step's integer checks
+        sph.upload(o.pos, o.vel, mass)
+    sph.close()
+
+
+# ------------------------------------------------------------------- full mode
+def _full_params(cfg, n, examine=96, variant=0, **kw):
+    sp = scenes.scene_params()
+    p = S.default_params(particle_count=n, grid=cfg["grid"], examine_count=examine, neighbor_mode=S.FULL,
+                         use_uniform_gravity=1, use_wall_collision=1, rho0=sp["rho0"], stiffness=sp["stiffness"],
+                         viscosity=sp["viscosity"], central_mass=0.0, gravity=sp["gravity"],
+                         time_step=sp["time_step"], kernel_variant=variant)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def _full_oracle(cfg, n, examine, p):
+    o = OracleSPH(n=n, grid=cfg["grid"], examine=examine, init_scene=False, rho0=p.rho0, stiffness=p.stiffness,
+                  viscosity=p.viscosity, central_mass=p.central_mass, gravity=list(p.gravity),
+                  time_step=p.time_step, damping=p.damping, cfl_limit=p.cfl_limit)
+    return o
+
+
+def _compare_full_step(sph, o, tag, check_lists=True):
+    d = sph.derived
+    assert np.array_equal(sph.download(F.VOXEL_ID), o.voxel_ids), tag
+    assert np.array_equal(sph.download(F.FINE_KEY), o.fine_keys), tag
+    cnt = sph.download(F.NEIGHBOR_COUNT)
+    assert np.array_equal(cnt, o.count), "%s: neighbour counts differ at %d particles" % (tag, (cnt != o.count).sum())
+    total, mx, mn = sph.neighbor_stats()
+    assert total == int(o.count.sum()) and mx == o.count.max() and mn == o.count.min()
+    if check_lists:
+        sph.build_neighbor_lists()
+        nb, nd = sparse_lists(sph.download(F.NEIGHBOR_INDEX), sph.download(F.NEIGHBOR_DISTANCE), o.count)
+        onb, ond = sparse_lists(o.nbr, o.dist, o.count)
+        assert np.array_equal(nb, onb), tag       # same sets, same (cell, index) order
+        assert np.array_equal(nd, ond), tag
+    check_density(sph.download(F.DENSITY), o.rho, w0_of(d, o.mass), tag)
+    check_acc(sph.download(F.ACCELERATION), o.acc, tag)
+    check_state(sph.download(F.POSITION), o.pos, 1.0, tag + " pos")
+    check_state(sph.download(F.VELOCITY), o.vel, 1.0, tag + " vel")
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["tiled", "flat"])
+def test_full_dambreak_vs_reference_golden(golden_full, variant):
+    g = golden_full
+    cfg = scenes.CONFIGS["dambreak_16k"]
+    n = g["pos0"].shape[0]
+    sph = S.SPH(_full_params(cfg, n, int(g["examine"]), variant), init_scene=False)
+    sph.upload(g["pos0"], g["vel0"])
+    d = sph.derived
+    sph.step_n(1)
+    assert np.array_equal(sph.download(F.VOXEL_ID), g["voxel_ids_1"])
+    assert np.array_equal(sph.download(F.FINE_KEY), g["fine_keys_1"])
+    cnt = sph.download(F.NEIGHBOR_COUNT)
+    assert np.array_equal(cnt, g["nbr_count_1"])
+    sph.build_neighbor_lists()
+    nb, _ = sparse_lists(sph.download(F.NEIGHBOR_INDEX), None, cnt)
+    assert np.array_equal(nb, g["nbr_idx_1"])
+    check_density(sph.download(F.DENSITY), g["density_1"], w0_of(d), "golden full")
+    check_acc(sph.download(F.ACCELERATION), g["acc_1"], "golden full")
+    check_state(sph.download(F.POSITION), g["pos_1"], 1.0)
+    check_state(sph.download(F.VELOCITY), g["vel_1"], 1.0)
+    sph.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["tiled", "flat"])
+@pytest.mark.parametrize("name,sigma", [("dambreak_16k", 0.0), ("dambreak_16k", 3.0), ("dambreak_128k", 1.0)])
+def test_full_steps_vs_oracle(name, sigma, variant):
+    cfg = scenes.CONFIGS[name]
+    nx, ny, nz = cfg["sites"]
+    n = nx * ny * nz
+    pos = scenes.lattice_scene(nx, ny, nz, scenes.lattice_spacing(0.1, 40))
+    vel = np.random.default_rng(11).normal(0, sigma, (n, 3)).astype(np.float32) if sigma else np.zeros((n, 3), np.float32)
+    mass = (np.random.default_rng(5).random(n) * 0.2 + 0.9).astype(np.float32)
+    p = _full_params(cfg, n, 96, variant)
+    sph = S.SPH(p, init_scene=False)
+    o = _full_oracle(cfg, n, 96, p)
+    sph.upload(pos, vel, mass)
+    o.set_state(pos, vel, mass)
+    for s in range(2):
+        o.step(O_FULL, True, True)
+        sph.step_n(1)
+        _compare_full_step(sph, o, "%s sigma=%g step %d" % (name, sigma, s))
+        sph.upload(o.pos, o.vel, mass)
+    sph.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["tiled", "flat"])
+def test_full_clumps_and_edges_vs_oracle(variant):
+    """Dense clumps (exercise tile sub-division and the global fallback), an
+    empty region, particles outside the box, coincident particles, one NaN."""
+    rng = np.random.default_rng(3)
+    grid = (12, 8, 8)
+    parts = [
+        rng.random((6000, 3)) * np.array([2.4, 1.6, 1.6]),                   # background gas
+        rng.normal(0, 0.10, (3000, 3)) + np.array([0.83, 0.79, 0.81]),       # very dense clump (global fallback)
+        rng.normal(0, 0.20, (4000, 3)) + np.array([1.6, 0.6, 1.0]),          # dense clump (sub-tiles)
+        rng.random((300, 3)) * 0.2 - 0.25,                                   # below the box
+        rng.random((300, 3)) * 0.2 + np.array([2.4, 1.6, 1.6]),              # above the box
+    ]
+    pos = np.concatenate(parts).astype(np.float32)
+    pos[100] = pos[101]                                                      # coincident pair
+    pos[200, 1] = np.nan
+    n = pos.shape[0]
+    vel = rng.normal(0, 1, (n, 3)).astype(np.float32)
+    cfg = dict(grid=grid)
+    p = _full_params(cfg, n, 1024, variant)
+    p.use_wall_collision = 0
+    sph = S.SPH(p, init_scene=False)
+    o = _full_oracle(cfg, n, 1024, p)
+    sph.upload(pos, vel)
+    o.set_state(pos, vel)
+    o.step(O_FULL, True, False)
+    sph.step_n(1)
+    assert o.count.max() > 400
+    _compare_full_step(sph, o, "clumps")
+    sph.close()
+
+
+def test_full_tiny_and_empty_systems():
+    cfg = dict(grid=(4, 4, 4))
+    for n in (0, 1, 2, 33):
+        p = _full_params(cfg, n, 32)
+        sph = S.SPH(p, init_scene=False)
+        pos = (np.random.default_rng(n).random((n, 3)) * 0.05 + 0.4).astype(np.float32)
+        vel = np.zeros((n, 3), np.float32)
+        sph.upload(pos, vel)
+        sph.step_n(2)
+        sph.synchronize()
+        if n:
+            o = _full_oracle(cfg, n, 32, p)
+            o.set_state(pos, vel)
+            o.step(O_FULL, True, True)
+            sph2 = S.SPH(p, init_scene=False)
+            sph2.upload(pos, vel)
+            sph2.step_n(1)
+            _compare_full_step(sph2, o, "tiny n=%d" % n)
+            sph2.close()
+        sph.close()
+
+
+def test_full_tiled_equals_flat_bitwise_on_integers_and_close_on_fields():
+    cfg = scenes.CONFIGS["dambreak_128k"]
+    nx, ny, nz = cfg["sites"]
+    n = nx * ny * nz
+    pos = scenes.lattice_scene(nx, ny, nz, scenes.lattice_spacing(0.1, 60))   # denser: ~60 neighbours
+    vel = np.zeros((n, 3), np.float32)
+    out = []
+    for variant in (0, 1):
+        sph = S.SPH(_full_params(cfg, n, 160, variant), init_scene=False)
+        sph.upload(pos, vel)
+        sph.step_n(3)
+        out.append((sph.download(F.NEIGHBOR_COUNT), sph.download(F.DENSITY), sph.download(F.POSITION),
+                    sph.energies()))
+        sph.close()
+    assert np.array_equal(out[0][0], out[1][0])
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-5)
+    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(out[0][3], out[1][3], rtol=1e-5)
+
+
+# ------------------------------------------------------------------ ABI errors
+def test_abi_error_paths():
+    sph = S.SPH()
+    with pytest.raises(S.SphError):
+        sph.download(F.FINE_KEY)                 # sampled context has no fine keys
+    with pytest.raises(S.SphError):
+        sph.set_params(grid=(16, 16, 16))        # structural field after create
+    with pytest.raises(S.SphError):
+        S.SPH(S.default_params(examine_count=4), init_scene=False)
+    sph.setStiffness(0.002)
+    sph.setCflLimit(123.0)
+    assert abs(sph.getStiffness() - 0.002) < 1e-9 and abs(sph.derived.cfl_limit2 - 123.0 ** 2) < 1e-3
+    assert sph.getParticleCount() == 32768 and sph.getGridCellCounts() == (32, 32, 32)
+    assert abs(sph.getCellSize() - 0.2) < 1e-6
+    sph.close()
+
+
+def test_step_host_roundtrip_matches_device_resident_path(golden_default):
+    g = golden_default
+    sph = S.SPH()
+    pos = g["pos0"].copy()
+    vel = g["vel0"].copy()
+    sph.step_host_ptr(pos.ctypes.data, vel.ctypes.data)
+    check_state(pos, g["pos_1"], 1.0)
+    check_state(vel, g["vel_1"], 1.0)
+    assert sph.launch_count() > 0
+    sph.close()
