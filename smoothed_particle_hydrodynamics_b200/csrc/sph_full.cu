@@ -8,15 +8,20 @@
 //   force sweep   : spiky pressure + viscosity (computeAcceleration,
 //                   sph.cpp:778-934) + integrate (937-1022) + wall collision
 //                   (1025-1148) + energy / neighbour statistics
-// No neighbour list is ever stored.  A CTA owns a 4x4x4 block of fine cells,
-// stages the block plus its one-cell halo (36 x-contiguous row segments of the
-// cell-sorted arrays) in shared memory, and each thread walks the 9 x-runs of
-// its particle there.  The force sweep separates the cheap distance test from
-// the expensive pair body through a per-thread ring of hit indices so that a
-// warp only executes pair bodies for real neighbours, in ascending cell order
-// (the order the in-loop viscosity scaling of sph.cpp:880-882 depends on).
+// A CTA owns a 4x4x4 block of fine cells, stages the block plus its one-cell halo
+// (36 x-contiguous row segments of the cell-sorted arrays) in shared memory, and
+// each thread walks the 9 x-runs of its particle there.
+//
+// The density sweep has to touch every candidate anyway, so it also records which
+// candidates passed a (slightly enlarged) radius test as a HIT-MASK STREAM: one
+// 8-byte record {32-bit mask, shared-memory byte offset of the chunk's first
+// candidate} per 32-candidate chunk that has a hit.  The force sweep stages the
+// same tile layout and simply walks the set bits of its particle's records -- no
+// second scan -- applying the exact reference test (sph.cpp:633-653) and the pair
+// body in ascending cell order (the order the in-loop viscosity scaling of
+// sph.cpp:880-882 depends on).  No per-particle neighbour list is stored.
 // Blocks too dense for shared memory are split (4x4x2, 4x2x2, 2x2x2) and, past
-// that, processed straight from global memory (same arithmetic).
+// that, processed straight from global memory (same arithmetic, scan based).
 #include "sph_math.cuh"
 
 namespace
@@ -27,9 +32,10 @@ constexpr int HROWS = (TB + 2) * (TB + 2);  // halo rows (y,z) of a full tile
 constexpr int CSW = TB + 3;                 // cell_start entries per halo row
 constexpr int TROWS = TB * TB;              // target rows of a full tile
 constexpr int kTileThreads = 256;
-constexpr int kCapDensity = 2560;           // staged particles, density sweep (16 B each)
-constexpr int kCapForce = 2400;             // staged particles, force sweep (32 B each)
-constexpr int QCAP = 64;                    // hit ring entries per thread (power of two)
+constexpr int kCap = 2400;                  // staged particles per (sub-)tile; BOTH sweeps must lay tiles out
+                                            // identically (stream offsets), so they share the capacity
+constexpr int WCAP = 32;                    // hit-mask records per particle (32 candidates each)
+constexpr unsigned kNoStream = 0xffu;       // info.nw value: no stream, scan instead
 constexpr int kFlatThreads = 128;
 
 struct TileLayout
@@ -56,6 +62,23 @@ __device__ __forceinline__ float density_term(float sum, float xi, float yi, flo
    return fmaf(pj.w * t, t * t, sum);
 }
 
+// single-instruction MUFU approximations (relative error <= 2^-22, far inside the
+// 1e-5 field tolerance; .ftz avoids the denormal pre/post scaling the default
+// sqrtf / __fdividef expand to).  sqrt(0) = 0 for coincident particles.
+__device__ __forceinline__ float sph_sqrt_approx(float x)
+{
+   float r;
+   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+   return r;
+}
+
+__device__ __forceinline__ float sph_rcp_approx(float x)
+{
+   float r;
+   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+   return r;
+}
+
 struct ForceI     // per-target constants of computeAcceleration (sph.cpp:785-798)
 {
    float x, y, z, vx, vy, vz;
@@ -63,23 +86,47 @@ struct ForceI     // per-target constants of computeAcceleration (sph.cpp:785-79
    float s;        // mu * rhoiInv   (in-loop viscosity scale, sph.cpp:880-882)
 };
 
-// one neighbour of computeAcceleration's loop (sph.cpp:825-884).  pj = (x,y,z,fA),
-// vj = (vx,vy,vz,fB) with fA, fB from sph_force_coeffs.  d2 is the exact squared
-// distance that passed the d2 < h2 test.
-__device__ __forceinline__ void force_pair(const DevParams& P, const ForceI& I, float4 pj, float4 vj, float d2,
-                                           Vec3& pg, Vec3& vt)
+// one neighbour of computeAcceleration's loop (sph.cpp:825-884).  (dx,dy,dz) =
+// r_i - r_j and d2 are the exactly rounded values of the neighbour test; fA, fB are
+// the neighbour's coefficients from sph_force_coeffs; (vx,vy,vz) its velocity.
+template <bool UNIT_SCALE>
+__device__ __forceinline__ void force_pair(const DevParams& P, const ForceI& I, float dx, float dy, float dz,
+                                           float d2, float fA, float vx, float vy, float vz, float fB, Vec3& pg,
+                                           Vec3& vt)
 {
-   float d = sqrtf(d2) * P.scale;
-   float inv = __fdividef(P.k2, d + 0.01f);
+   float d = sph_sqrt_approx(d2);
+   if (!UNIT_SCALE)
+   {
+      d *= P.scale;
+      dx *= P.scale;
+      dy *= P.scale;
+      dz *= P.scale;
+   }
+   float inv = P.k2 * sph_rcp_approx(d + 0.01f);
    float hd = P.hs - d;
-   float c = (hd * hd) * (I.pi_div * pj.w) * inv;
-   pg.x = fmaf((I.x - pj.x) * P.scale, c, pg.x);
-   pg.y = fmaf((I.y - pj.y) * P.scale, c, pg.y);
-   pg.z = fmaf((I.z - pj.z) * P.scale, c, pg.z);
-   float cv = hd * vj.w;
-   vt.x = fmaf(vj.x - I.vx, cv, vt.x) * I.s;
-   vt.y = fmaf(vj.y - I.vy, cv, vt.y) * I.s;
-   vt.z = fmaf(vj.z - I.vz, cv, vt.z) * I.s;
+   float c = (hd * hd) * (I.pi_div * fA) * inv;
+   pg.x = fmaf(dx, c, pg.x);
+   pg.y = fmaf(dy, c, pg.y);
+   pg.z = fmaf(dz, c, pg.z);
+   float cv = hd * fB;
+   vt.x = fmaf(vx - I.vx, cv, vt.x) * I.s;
+   vt.y = fmaf(vy - I.vy, cv, vt.y) * I.s;
+   vt.z = fmaf(vz - I.vz, cv, vt.z) * I.s;
+}
+
+// exact test + pair body for candidate (pj, vj); returns 1 when it is a neighbour
+template <bool UNIT_SCALE>
+__device__ __forceinline__ int force_candidate(const DevParams& P, const ForceI& I, float4 pj, float4 vj,
+                                               bool not_self, Vec3& pg, Vec3& vt)
+{
+   float dx = __fsub_rn(I.x, pj.x), dy = __fsub_rn(I.y, pj.y), dz = __fsub_rn(I.z, pj.z);
+   float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));   // sph.cpp:641
+   if (d2 < P.h2 && not_self)
+   {
+      force_pair<UNIT_SCALE>(P, I, dx, dy, dz, d2, pj.w, vj.x, vj.y, vj.z, vj.w, pg, vt);
+      return 1;
+   }
+   return 0;
 }
 
 __device__ __forceinline__ ForceI make_force_i(const DevParams& P, float4 pi, float4 vi, float rho)
@@ -101,8 +148,10 @@ __device__ __forceinline__ void density_store(const DevParams& P, int k, float4 
                                               float4* __restrict__ s_velB4, float* __restrict__ s_rho)
 {
    // the particle itself sat in the centre run at d2 = 0: remove its own term
-   // (the reference skips realIndex == particleIndex, sph.cpp:737)
-   float self = __fmul_rn(pi.w * P.hs2, P.hs2 * P.hs2);
+   // (the reference skips realIndex == particleIndex, sph.cpp:737).  Evaluated
+   // through the same expression so that a NaN position (term 0) stays consistent
+   // and an isolated particle gets exactly 0.
+   float self = density_term(0.0f, pi.x, pi.y, pi.z, pi, P.hs2, P.scale * P.scale);
    float rho = P.k1 * (sum - self);
    float fA, fB;
    sph_force_coeffs(P, rho, pi.w, fA, fB);
@@ -211,12 +260,7 @@ __global__ void __launch_bounds__(kFlatThreads)
          for (int j = b[r]; j < e[r]; j++)
          {
             float4 pj = __ldg(&s_posA4[j]);
-            float d2 = sph_dist2_exact(I.x, I.y, I.z, pj.x, pj.y, pj.z);
-            if (d2 < P.h2 && j != k)
-            {
-               force_pair(P, I, pj, __ldg(&s_velB4[j]), d2, pg, vt);
-               count++;
-            }
+            count += force_candidate<false>(P, I, pj, __ldg(&s_velB4[j]), j != k, pg, vt);
          }
       force_store(P, k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, ek, ep);
       cnt = (unsigned long long)count;
@@ -428,35 +472,70 @@ __device__ int tile_population(const DevParams& P, int X0, int Y0, int Z0, const
    return warp_sum(sum);
 }
 
+// hit-mask stream addressing: the records of 32 consecutive sorted particles are
+// interleaved so that a warp's lanes write / read 256 contiguous bytes per record
+__device__ __forceinline__ size_t stream_base(int k)
+{
+   return ((size_t)(k >> 5) * WCAP) * 32 + (size_t)(k & 31);
+}
+
+// Density sweep over one (sub-)tile.  STAGED: candidates come from shared memory
+// and the hit-mask stream is written; otherwise candidates come from global
+// memory and the particle is flagged "scan me" for the force sweep.
 template <bool STAGED>
 __device__ __forceinline__ void density_targets(const DevParams& P, const SubTile& t, const TileLayout& L,
                                                 const float4* __restrict__ src,
                                                 const uint32_t* __restrict__ idx_sorted,
                                                 const float4* __restrict__ vel4, float4* __restrict__ s_posA4,
-                                                float4* __restrict__ s_velB4, float* __restrict__ s_rho)
+                                                float4* __restrict__ s_velB4, float* __restrict__ s_rho,
+                                                uint2* __restrict__ hit_rec, unsigned* __restrict__ hit_info)
 {
    const float scale2 = P.scale * P.scale;
+   const float tmin = -1e-5f * P.hs2;      // enlarged radius: a superset of the exact d2 < h2 test
    for (int tnum = threadIdx.x; tnum < L.ntargets; tnum += blockDim.x)
    {
       Target T = locate_target(t, L, tnum);
-      float4 pi = src[T.k + L.row_delta[T.hr0]];
+      const float4 pi = src[T.k + L.row_delta[T.hr0]];
+      uint2* rec = hit_rec + stream_base(T.k);
       float sum = 0.0f;
-#pragma unroll
-      for (int dz = -1; dz <= 1; dz++)
-#pragma unroll
-         for (int dy = -1; dy <= 1; dy++)
+      int nw = 0, nhits = 0;
+#pragma unroll 1
+      for (int r = 0; r < 9; r++)
+      {
+         int hr = T.hr0 + (r / 3 - 1) * (t.by + 2) + (r - (r / 3) * 3 - 1);
+         int delta = L.row_delta[hr];
+         int b = L.cs[hr][T.lx - 1] + delta;
+         int e = L.cs[hr][T.lx + 2] + delta;
+#pragma unroll 1
+         for (int c0 = b; c0 < e; c0 += 32)
          {
-            int hr = T.hr0 + dz * (t.by + 2) + dy;
-            int delta = L.row_delta[hr];
-            int b = L.cs[hr][T.lx - 1] + delta;
-            int e = L.cs[hr][T.lx + 2] + delta;
+            const float4* p = src + c0;
+            const float4* pe = src + min(c0 + 32, e);
+            unsigned mask = 0, bit = 1;
 #pragma unroll 4
-            for (int j = b; j < e; j++)
+            for (; p < pe; p++, bit <<= 1)
             {
-               float4 pj = STAGED ? src[j] : __ldg(&src[j]);
-               sum = density_term(sum, pi.x, pi.y, pi.z, pj, P.hs2, scale2);
+               float4 pj = STAGED ? *p : __ldg(p);
+               float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+               float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+               float tt = fmaf(-d2, scale2, P.hs2);
+               mask |= (tt > tmin) ? bit : 0u;
+               float tc = fmaxf(tt, 0.0f);
+               sum = fmaf(pj.w * tc, tc * tc, sum);
+            }
+            if (STAGED && mask != 0u)
+            {
+               if (nw < WCAP)
+                  rec[(size_t)nw * 32] = make_uint2(mask, (unsigned)(c0 * 16));
+               nw++;
+               nhits += __popc(mask);
             }
          }
+      }
+      if (STAGED)
+         hit_info[T.k] = nw <= WCAP ? ((unsigned)nw | ((unsigned)nhits << 8)) : kNoStream;
+      else
+         hit_info[T.k] = kNoStream;
       density_store(P, T.k, pi, sum, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
    }
 }
@@ -464,7 +543,8 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
 __global__ void __launch_bounds__(kTileThreads)
    k_density_tiled(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ cell_start,
                    const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ vel4,
-                   float4* __restrict__ s_posA4, float4* __restrict__ s_velB4, float* __restrict__ s_rho)
+                   float4* __restrict__ s_posA4, float4* __restrict__ s_velB4, float* __restrict__ s_rho,
+                   uint2* __restrict__ hit_rec, unsigned* __restrict__ hit_info)
 {
    extern __shared__ __align__(16) unsigned char smem_raw[];
    float4* sp = reinterpret_cast<float4*>(smem_raw);
@@ -475,7 +555,7 @@ __global__ void __launch_bounds__(kTileThreads)
    if (threadIdx.x < 32)
    {
       int pop = tile_population(P, X0, Y0, Z0, cell_start);
-      int level = pop > 0 ? choose_level(P, X0, Y0, Z0, cell_start, kCapDensity) : 0;
+      int level = pop > 0 ? choose_level(P, X0, Y0, Z0, cell_start, kCap) : 0;
       if (threadIdx.x == 0)
       {
          s_pop = pop;
@@ -501,44 +581,132 @@ __global__ void __launch_bounds__(kTileThreads)
                {
                   stage_rows(t, L, s_pos4, sp);
                   __syncthreads();
-                  density_targets<true>(P, t, L, sp, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
+                  density_targets<true>(P, t, L, sp, idx_sorted, vel4, s_posA4, s_velB4, s_rho, hit_rec, hit_info);
                }
                else
-                  density_targets<false>(P, t, L, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
+                  density_targets<false>(P, t, L, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho, hit_rec,
+                                         hit_info);
             }
             __syncthreads();   // smem and layout are reused by the next sub-tile
          }
 }
 
-// drains up to `n` queued hits of this lane (n is warp-uniform)
-__device__ __forceinline__ void drain_hits(const DevParams& P, const ForceI& I, const float4* __restrict__ spA,
-                                           const float4* __restrict__ svB, const unsigned short* __restrict__ q,
-                                           int& qh, int qt, int n, Vec3& pg, Vec3& vt)
+// scan-based force loop for one target (dense fallbacks): candidates from `srcA`
+// / `srcB` (shared or global), runs from the layout tables
+template <bool UNIT_SCALE, bool STAGED>
+__device__ __forceinline__ int force_scan_target(const DevParams& P, const SubTile& t, const TileLayout& L,
+                                                 const Target& T, const ForceI& I, const float4* __restrict__ srcA,
+                                                 const float4* __restrict__ srcB, Vec3& pg, Vec3& vt)
 {
-   for (int it = 0; it < n; it++)
+   int count = 0;
+   const int self = T.k + (STAGED ? L.row_delta[T.hr0] : 0);
+#pragma unroll 1
+   for (int r = 0; r < 9; r++)
    {
-      if (qh < qt)
+      int hr = T.hr0 + (r / 3 - 1) * (t.by + 2) + (r - (r / 3) * 3 - 1);
+      int delta = STAGED ? L.row_delta[hr] : 0;
+      int b = L.cs[hr][T.lx - 1] + delta, e = L.cs[hr][T.lx + 2] + delta;
+      for (int j = b; j < e; j++)
       {
-         int j = q[(qh & (QCAP - 1)) * kTileThreads];
-         qh++;
-         float4 pj = spA[j];
-         float d2 = sph_dist2_exact(I.x, I.y, I.z, pj.x, pj.y, pj.z);
-         force_pair(P, I, pj, svB[j], d2, pg, vt);
+         float4 pj = STAGED ? srcA[j] : __ldg(&srcA[j]);
+         float4 vj = STAGED ? srcB[j] : __ldg(&srcB[j]);
+         count += force_candidate<UNIT_SCALE>(P, I, pj, vj, j != self, pg, vt);
+      }
+   }
+   return count;
+}
+
+// Force sweep over the staged sub-tile, driven by the hit-mask stream of the
+// density sweep: each lane walks the set bits of its particle's records (ascending
+// = cell order); all lanes of a warp iterate to the warp's largest hit count.
+template <bool UNIT_SCALE>
+__device__ __forceinline__ void force_targets_staged(const DevParams& P, const SubTile& t, const TileLayout& L,
+                                                     const unsigned char* __restrict__ smemA, int offB,
+                                                     const float4* __restrict__ s_pos4,
+                                                     const float* __restrict__ s_rho,
+                                                     const uint32_t* __restrict__ idx_sorted,
+                                                     const uint2* __restrict__ hit_rec,
+                                                     const unsigned* __restrict__ hit_info,
+                                                     float4* __restrict__ pos4, float4* __restrict__ vel4,
+                                                     float4* __restrict__ s_acc4, int* __restrict__ s_count,
+                                                     double& ek, double& ep, unsigned long long& cnt, int& cmax,
+                                                     int& cmin)
+{
+   const int rounds = (L.ntargets + kTileThreads - 1) / kTileThreads;
+#pragma unroll 1
+   for (int round = 0; round < rounds; round++)
+   {
+      const int tnum = round * kTileThreads + threadIdx.x;
+      const bool active = tnum < L.ntargets;
+      Target T = locate_target(t, L, active ? tnum : 0);
+      const int self_off = (T.k + L.row_delta[T.hr0]) * 16;
+      const float4 pi = *reinterpret_cast<const float4*>(smemA + self_off);
+      const float4 vi = *reinterpret_cast<const float4*>(smemA + offB + self_off);
+      ForceI I = make_force_i(P, pi, vi, s_rho[T.k]);
+      Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
+      int count = 0;
+      const unsigned info = active ? hit_info[T.k] : 0u;
+      const bool scan = (info & 0xffu) == kNoStream;
+      const int nw = scan ? 0 : (int)(info & 0xffu);
+      const int nhits = scan ? 0 : (int)(info >> 8);
+      const uint2* rec = hit_rec + stream_base(T.k);
+      int w = 0;
+      unsigned m = 0;
+      int base = 0;
+      uint2 nxt = make_uint2(0u, 0u);
+      if (nw > 0)
+         nxt = __ldg(rec);
+      const int nmax = __reduce_max_sync(0xffffffffu, nhits);
+#pragma unroll 1
+      for (int it = 0; it < nmax; it++)
+      {
+         if (it < nhits)
+         {
+            if (m == 0u)
+            {
+               // next record (records with an empty mask are never stored); prefetch the one after
+               m = nxt.x;
+               base = (int)nxt.y;
+               w++;
+               if (w < nw)
+                  nxt = __ldg(rec + (size_t)w * 32);
+            }
+            int bit = __ffs((int)m) - 1;
+            m &= m - 1u;
+            int off = base + bit * 16;
+            float4 pj = *reinterpret_cast<const float4*>(smemA + off);
+            float4 vj = *reinterpret_cast<const float4*>(smemA + offB + off);
+            count += force_candidate<UNIT_SCALE>(P, I, pj, vj, off != self_off, pg, vt);
+         }
+      }
+      if (scan && active)   // record capacity exceeded in the density sweep: scan the staged runs instead
+         count = force_scan_target<UNIT_SCALE, true>(P, t, L, T, I, reinterpret_cast<const float4*>(smemA),
+                                                    reinterpret_cast<const float4*>(smemA + offB), pg, vt);
+      if (active)
+      {
+         double e1, e2;
+         force_store(P, T.k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, e1, e2);
+         ek += e1;
+         ep += e2;
+         cnt += (unsigned long long)count;
+         cmax = max(cmax, count);
+         cmin = min(cmin, count);
       }
    }
 }
 
+template <bool UNIT_SCALE>
 __global__ void __launch_bounds__(kTileThreads)
    k_force_tiled(DevParams P, const float4* __restrict__ s_pos4, const float4* __restrict__ s_posA4,
                  const float4* __restrict__ s_velB4, const float* __restrict__ s_rho,
                  const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ idx_sorted,
+                 const uint2* __restrict__ hit_rec, const unsigned* __restrict__ hit_info,
                  float4* __restrict__ pos4, float4* __restrict__ vel4, float4* __restrict__ s_acc4,
                  int* __restrict__ s_count, double* __restrict__ block_partials, StepScalars* scal)
 {
    extern __shared__ __align__(16) unsigned char smem_raw[];
    float4* spA = reinterpret_cast<float4*>(smem_raw);
-   float4* svB = spA + kCapForce;
-   unsigned short* queue = reinterpret_cast<unsigned short*>(svB + kCapForce);
+   float4* svB = spA + kCap;
    __shared__ TileLayout L;
    __shared__ int s_level, s_pop;
    int X0, Y0, Z0;
@@ -546,7 +714,7 @@ __global__ void __launch_bounds__(kTileThreads)
    if (threadIdx.x < 32)
    {
       int pop = tile_population(P, X0, Y0, Z0, cell_start);
-      int level = pop > 0 ? choose_level(P, X0, Y0, Z0, cell_start, kCapForce) : 0;
+      int level = pop > 0 ? choose_level(P, X0, Y0, Z0, cell_start, kCap) : 0;
       if (threadIdx.x == 0)
       {
          s_pop = pop;
@@ -563,8 +731,6 @@ __global__ void __launch_bounds__(kTileThreads)
    const int bz = (level >= 1 && level < 4) ? TB / 2 : TB;
    const int by = (level >= 2 && level < 4) ? TB / 2 : TB;
    const int bx = (level >= 3 && level < 4) ? TB / 2 : TB;
-   const unsigned short* q = queue + threadIdx.x;
-   unsigned short* qw = queue + threadIdx.x;
    for (int z = 0; z < TB; z += bz)
       for (int y = 0; y < TB; y += by)
          for (int x = 0; x < TB; x += bx)
@@ -576,62 +742,9 @@ __global__ void __launch_bounds__(kTileThreads)
                stage_rows(t, L, s_posA4, spA);
                stage_rows(t, L, s_velB4, svB);
                __syncthreads();
-               // all lanes of a warp run the same number of outer iterations so
-               // that the warp-wide reductions below are convergent
-               int rounds = (L.ntargets + blockDim.x - 1) / blockDim.x;
-               for (int round = 0; round < rounds; round++)
-               {
-                  int tnum = round * blockDim.x + threadIdx.x;
-                  bool active = tnum < L.ntargets;
-                  Target T = locate_target(t, L, active ? tnum : 0);
-                  int self = T.k + L.row_delta[T.hr0];
-                  ForceI I = make_force_i(P, spA[self], svB[self], s_rho[T.k]);
-                  Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
-                  int qh = 0, qt = 0;
-#pragma unroll
-                  for (int dz = -1; dz <= 1; dz++)
-#pragma unroll
-                     for (int dy = -1; dy <= 1; dy++)
-                     {
-                        int hr = T.hr0 + dz * (t.by + 2) + dy;
-                        int delta = L.row_delta[hr];
-                        int b = L.cs[hr][T.lx - 1] + delta;
-                        int e = active ? L.cs[hr][T.lx + 2] + delta : b;
-                        int chunks = __reduce_max_sync(0xffffffffu, (e - b + 31) >> 5);
-                        for (int c = 0; c < chunks; c++)
-                        {
-                           // make room for 32 more hits in every lane's ring
-                           int need = __reduce_max_sync(0xffffffffu, (qt - qh) + 32 - QCAP);
-                           if (need > 0)
-                              drain_hits(P, I, spA, svB, q, qh, qt, need, pg, vt);
-                           int j0 = b + c * 32;
-                           int j1 = min(j0 + 32, e);
-#pragma unroll 4
-                           for (int j = j0; j < j1; j++)
-                           {
-                              float4 pj = spA[j];
-                              float d2 = sph_dist2_exact(I.x, I.y, I.z, pj.x, pj.y, pj.z);
-                              if (d2 < P.h2 && j != self)
-                              {
-                                 qw[(qt & (QCAP - 1)) * kTileThreads] = (unsigned short)j;
-                                 qt++;
-                              }
-                           }
-                        }
-                     }
-                  int rest = __reduce_max_sync(0xffffffffu, qt - qh);
-                  drain_hits(P, I, spA, svB, q, qh, qt, rest, pg, vt);
-                  if (active)
-                  {
-                     double e1, e2;
-                     force_store(P, T.k, I, vt, pg, qt, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, e1, e2);
-                     ek += e1;
-                     ep += e2;
-                     cnt += (unsigned long long)qt;
-                     cmax = max(cmax, qt);
-                     cmin = min(cmin, qt);
-                  }
-               }
+               force_targets_staged<UNIT_SCALE>(P, t, L, smem_raw, (int)(sizeof(float4) * kCap), s_pos4, s_rho,
+                                                idx_sorted, hit_rec, hit_info, pos4, vel4, s_acc4, s_count, ek, ep,
+                                                cnt, cmax, cmin);
             }
             else if (L.ntargets > 0)
             {
@@ -641,23 +754,7 @@ __global__ void __launch_bounds__(kTileThreads)
                   Target T = locate_target(t, L, tnum);
                   ForceI I = make_force_i(P, s_posA4[T.k], s_velB4[T.k], s_rho[T.k]);
                   Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
-                  int count = 0;
-                  for (int dz = -1; dz <= 1; dz++)
-                     for (int dy = -1; dy <= 1; dy++)
-                     {
-                        int hr = T.hr0 + dz * (t.by + 2) + dy;
-                        int b = L.cs[hr][T.lx - 1], e = L.cs[hr][T.lx + 2];
-                        for (int j = b; j < e; j++)
-                        {
-                           float4 pj = __ldg(&s_posA4[j]);
-                           float d2 = sph_dist2_exact(I.x, I.y, I.z, pj.x, pj.y, pj.z);
-                           if (d2 < P.h2 && j != T.k)
-                           {
-                              force_pair(P, I, pj, __ldg(&s_velB4[j]), d2, pg, vt);
-                              count++;
-                           }
-                        }
-                     }
+                  int count = force_scan_target<UNIT_SCALE, false>(P, t, L, T, I, s_posA4, s_velB4, pg, vt);
                   double e1, e2;
                   force_store(P, T.k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, e1, e2);
                   ek += e1;
@@ -727,8 +824,8 @@ __global__ void __launch_bounds__(kFlatThreads)
    nbr_count[o] = s_count[k];
 }
 
-size_t density_smem() { return sizeof(float4) * (size_t)kCapDensity; }
-size_t force_smem() { return sizeof(float4) * 2 * (size_t)kCapForce + sizeof(unsigned short) * QCAP * kTileThreads; }
+size_t density_smem() { return sizeof(float4) * (size_t)kCap; }
+size_t force_smem() { return sizeof(float4) * 2 * (size_t)kCap; }
 
 }  // namespace
 
@@ -736,8 +833,14 @@ int sph_full_configure(sphb200_ctx* ctx)
 {
    SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)density_smem()));
-   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_force_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_force_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)force_smem()));
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_force_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)force_smem()));
+   // hit-mask stream: WCAP records per particle, interleaved per 32 sorted particles
+   size_t groups = ((size_t)ctx->capacity + 31) / 32;
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->hit_rec, sizeof(uint2) * (groups ? groups : 1) * WCAP * 32));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->hit_info, sizeof(unsigned) * (size_t)(ctx->capacity + 1)));
    return SPHB200_OK;
 }
 
@@ -772,13 +875,18 @@ int sph_step_full(sphb200_ctx* ctx)
       SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_block_partials, 0, sizeof(double) * 2 * (size_t)blocks, st));
       k_density_tiled<<<blocks, kTileThreads, density_smem(), st>>>(P, ctx->s_pos4, ctx->cell_start,
                                                                    ctx->idx_sorted, ctx->vel4, ctx->s_posA4,
-                                                                   ctx->s_velB4, ctx->s_rho);
+                                                                   ctx->s_velB4, ctx->s_rho, ctx->hit_rec,
+                                                                   ctx->hit_info);
       if (timed) cudaEventRecord(ctx->ev[3], st);
       if (timed) cudaEventRecord(ctx->ev[4], st);
-      k_force_tiled<<<blocks, kTileThreads, force_smem(), st>>>(P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4,
-                                                               ctx->s_rho, ctx->cell_start, ctx->idx_sorted,
-                                                               ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count,
-                                                               ctx->d_block_partials, ctx->d_scalars);
+      if (P.scale == 1.0f)
+         k_force_tiled<true><<<blocks, kTileThreads, force_smem(), st>>>(
+            P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->cell_start, ctx->idx_sorted, ctx->hit_rec,
+            ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials, ctx->d_scalars);
+      else
+         k_force_tiled<false><<<blocks, kTileThreads, force_smem(), st>>>(
+            P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->cell_start, ctx->idx_sorted, ctx->hit_rec,
+            ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials, ctx->d_scalars);
    }
    else
    {

@@ -76,6 +76,8 @@ struct sphb200_ctx
    float* s_rho;          // sorted density
    float4* s_acc4;        // sorted acceleration (x,y,z,unused)
    int* s_count;          // sorted neighbour count
+   uint2* hit_rec;        // FULL mode hit-mask stream {mask, smem byte offset}, see sph_full.cu
+   unsigned* hit_info;    // per sorted particle: records | hits << 8, or 0xff = scan
 
    // SAMPLED mode / on-demand lists, original order
    uint32_t* nbr_idx;     // N * E
