@@ -36,6 +36,8 @@ constexpr int kCap = 2400;                  // staged particles per (sub-)tile; 
                                             // identically (stream offsets), so they share the capacity
 constexpr int WCAP = 32;                    // hit-mask records per particle (32 candidates each)
 constexpr unsigned kNoStream = 0xffu;       // info.nw value: no stream, scan instead
+constexpr int RSM = 16;                     // records per thread kept in shared memory by the force sweep
+constexpr int kForceThreads = 128;
 constexpr int kFlatThreads = 128;
 
 struct TileLayout
@@ -112,6 +114,58 @@ __device__ __forceinline__ void force_pair(const DevParams& P, const ForceI& I, 
    vt.x = fmaf(vx - I.vx, cv, vt.x) * I.s;
    vt.y = fmaf(vy - I.vy, cv, vt.y) * I.s;
    vt.z = fmaf(vz - I.vz, cv, vt.z) * I.s;
+}
+
+// The same pair arithmetic split into an order-free part (force_term) and the
+// ordered accumulation (force_accumulate) so that two candidates can be in flight.
+struct PairTerm
+{
+   float px, py, pz;   // pressure-gradient contribution
+   float wx, wy, wz;   // viscous contribution before the in-loop scaling
+   int hit;
+};
+
+template <bool UNIT_SCALE>
+__device__ __forceinline__ PairTerm force_term(const DevParams& P, const ForceI& I, float4 pj, float4 vj,
+                                               bool not_self)
+{
+   float dx = __fsub_rn(I.x, pj.x), dy = __fsub_rn(I.y, pj.y), dz = __fsub_rn(I.z, pj.z);
+   float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));   // sph.cpp:641
+   PairTerm t;
+   t.hit = (d2 < P.h2 && not_self) ? 1 : 0;
+   float d = sph_sqrt_approx(d2);
+   if (!UNIT_SCALE)
+   {
+      d *= P.scale;
+      dx *= P.scale;
+      dy *= P.scale;
+      dz *= P.scale;
+   }
+   float inv = P.k2 * sph_rcp_approx(d + 0.01f);
+   float hd = P.hs - d;
+   float c = (hd * hd) * (I.pi_div * pj.w) * inv;
+   t.px = dx * c;
+   t.py = dy * c;
+   t.pz = dz * c;
+   float cv = hd * vj.w;
+   t.wx = (vj.x - I.vx) * cv;
+   t.wy = (vj.y - I.vy) * cv;
+   t.wz = (vj.z - I.vz) * cv;
+   return t;
+}
+
+__device__ __forceinline__ void force_accumulate(const ForceI& I, const PairTerm& t, Vec3& pg, Vec3& vt, int& count)
+{
+   if (t.hit)
+   {
+      pg.x += t.px;
+      pg.y += t.py;
+      pg.z += t.pz;
+      vt.x = (vt.x + t.wx) * I.s;      // sph.cpp:875-882: scaled inside the loop
+      vt.y = (vt.y + t.wy) * I.s;
+      vt.z = (vt.z + t.wz) * I.s;
+      count++;
+   }
 }
 
 // exact test + pair body for candidate (pj, vj); returns 1 when it is a neighbour
@@ -219,11 +273,12 @@ __global__ void __launch_bounds__(kFlatThreads)
    k_density_flat(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ keys_sorted,
                   const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ idx_sorted,
                   const float4* __restrict__ vel4, float4* __restrict__ s_posA4, float4* __restrict__ s_velB4,
-                  float* __restrict__ s_rho)
+                  float* __restrict__ s_rho, unsigned* __restrict__ hit_info)
 {
    int k = blockIdx.x * blockDim.x + threadIdx.x;
    if (k >= P.n)
       return;
+   hit_info[k] = kNoStream;   // the force sweep scans for these particles
    float4 pi = s_pos4[k];
    int b[9], e[9];
    global_runs(P, keys_sorted[k], cell_start, b, e);
@@ -234,40 +289,6 @@ __global__ void __launch_bounds__(kFlatThreads)
       for (int j = b[r]; j < e[r]; j++)
          sum = density_term(sum, pi.x, pi.y, pi.z, __ldg(&s_pos4[j]), P.hs2, scale2);
    density_store(P, k, pi, sum, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
-}
-
-__global__ void __launch_bounds__(kFlatThreads)
-   k_force_flat(DevParams P, const float4* __restrict__ s_pos4, const float4* __restrict__ s_posA4,
-                const float4* __restrict__ s_velB4, const float* __restrict__ s_rho,
-                const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ cell_start,
-                const uint32_t* __restrict__ idx_sorted, float4* __restrict__ pos4, float4* __restrict__ vel4,
-                float4* __restrict__ s_acc4, int* __restrict__ s_count, double* __restrict__ block_partials,
-                StepScalars* scal)
-{
-   int k = blockIdx.x * blockDim.x + threadIdx.x;
-   double ek = 0.0, ep = 0.0;
-   unsigned long long cnt = 0;
-   int cmax = -1, cmin = 0x7fffffff;
-   if (k < P.n)
-   {
-      ForceI I = make_force_i(P, s_posA4[k], s_velB4[k], s_rho[k]);
-      int b[9], e[9];
-      global_runs(P, keys_sorted[k], cell_start, b, e);
-      Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
-      int count = 0;
-#pragma unroll
-      for (int r = 0; r < 9; r++)
-         for (int j = b[r]; j < e[r]; j++)
-         {
-            float4 pj = __ldg(&s_posA4[j]);
-            count += force_candidate<false>(P, I, pj, __ldg(&s_velB4[j]), j != k, pg, vt);
-         }
-      force_store(P, k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, ek, ep);
-      cnt = (unsigned long long)count;
-      cmax = count;
-      cmin = count;
-   }
-   sph_block_reduce_scalars(ek, ep, cnt, cmax, cmin, block_partials, scal);
 }
 
 // ---- tiled kernels -----------------------------------------------------------
@@ -491,7 +512,7 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
                                                 uint2* __restrict__ hit_rec, unsigned* __restrict__ hit_info)
 {
    const float scale2 = P.scale * P.scale;
-   const float tmin = -1e-5f * P.hs2;      // enlarged radius: a superset of the exact d2 < h2 test
+   const float neg_lim = -1.00001f * P.hs2;   // enlarged radius: a superset of the exact d2 < h2 test
    for (int tnum = threadIdx.x; tnum < L.ntargets; tnum += blockDim.x)
    {
       Target T = locate_target(t, L, tnum);
@@ -510,23 +531,28 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
          for (int c0 = b; c0 < e; c0 += 32)
          {
             const float4* p = src + c0;
-            const float4* pe = src + min(c0 + 32, e);
-            unsigned mask = 0, bit = 1;
+            const int n = min(32, e - c0);
+            const float4* pe = p + n;
+            // hit bit of a candidate = sign bit of (d2*scale^2 - hs2 + tmin) < 0, shifted
+            // into the mask MSB-first: after the chunk candidate i sits at bit 31 - i
+            unsigned mask = 0;
 #pragma unroll 4
-            for (; p < pe; p++, bit <<= 1)
+            for (; p < pe; p++)
             {
                float4 pj = STAGED ? *p : __ldg(p);
                float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
                float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
                float tt = fmaf(-d2, scale2, P.hs2);
-               mask |= (tt > tmin) ? bit : 0u;
+               float u = fmaf(d2, scale2, neg_lim);
+               mask = __funnelshift_l(__float_as_uint(u), mask, 1);
                float tc = fmaxf(tt, 0.0f);
                sum = fmaf(pj.w * tc, tc * tc, sum);
             }
+            mask <<= (32 - n);
             if (STAGED && mask != 0u)
             {
                if (nw < WCAP)
-                  rec[(size_t)nw * 32] = make_uint2(mask, (unsigned)(c0 * 16));
+                  rec[(size_t)nw * 32] = make_uint2(mask, (unsigned)(c0 - delta));
                nw++;
                nhits += __popc(mask);
             }
@@ -540,7 +566,7 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
    }
 }
 
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, 4)
    k_density_tiled(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ cell_start,
                    const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ vel4,
                    float4* __restrict__ s_posA4, float4* __restrict__ s_velB4, float* __restrict__ s_rho,
@@ -591,181 +617,114 @@ __global__ void __launch_bounds__(kTileThreads)
          }
 }
 
-// scan-based force loop for one target (dense fallbacks): candidates from `srcA`
-// / `srcB` (shared or global), runs from the layout tables
-template <bool UNIT_SCALE, bool STAGED>
-__device__ __forceinline__ int force_scan_target(const DevParams& P, const SubTile& t, const TileLayout& L,
-                                                 const Target& T, const ForceI& I, const float4* __restrict__ srcA,
-                                                 const float4* __restrict__ srcB, Vec3& pg, Vec3& vt)
-{
-   int count = 0;
-   const int self = T.k + (STAGED ? L.row_delta[T.hr0] : 0);
-#pragma unroll 1
-   for (int r = 0; r < 9; r++)
-   {
-      int hr = T.hr0 + (r / 3 - 1) * (t.by + 2) + (r - (r / 3) * 3 - 1);
-      int delta = STAGED ? L.row_delta[hr] : 0;
-      int b = L.cs[hr][T.lx - 1] + delta, e = L.cs[hr][T.lx + 2] + delta;
-      for (int j = b; j < e; j++)
-      {
-         float4 pj = STAGED ? srcA[j] : __ldg(&srcA[j]);
-         float4 vj = STAGED ? srcB[j] : __ldg(&srcB[j]);
-         count += force_candidate<UNIT_SCALE>(P, I, pj, vj, j != self, pg, vt);
-      }
-   }
-   return count;
-}
-
-// Force sweep over the staged sub-tile, driven by the hit-mask stream of the
-// density sweep: each lane walks the set bits of its particle's records (ascending
-// = cell order); all lanes of a warp iterate to the warp's largest hit count.
+// Force sweep: one thread per cell-sorted particle, no shared-memory staging and
+// no block barriers before the final reduction.  The hit-mask stream of the
+// density sweep names the candidates that passed the enlarged radius test; each
+// lane walks the set bits of its records (MSB first = ascending cell order),
+// gathers that neighbour's (x,y,z,fA) / (vx,vy,vz,fB) through L1 and applies the
+// exact reference test and the pair body.  Consecutive lanes are consecutive
+// particles of a cell row, so their neighbour sets overlap and the gathers hit L1.
+// Particles without a stream (dense fallback tiles, record overflow, or the flat
+// density kernel) scan their 27 cells instead.
 template <bool UNIT_SCALE>
-__device__ __forceinline__ void force_targets_staged(const DevParams& P, const SubTile& t, const TileLayout& L,
-                                                     const unsigned char* __restrict__ smemA, int offB,
-                                                     const float4* __restrict__ s_pos4,
-                                                     const float* __restrict__ s_rho,
-                                                     const uint32_t* __restrict__ idx_sorted,
-                                                     const uint2* __restrict__ hit_rec,
-                                                     const unsigned* __restrict__ hit_info,
-                                                     float4* __restrict__ pos4, float4* __restrict__ vel4,
-                                                     float4* __restrict__ s_acc4, int* __restrict__ s_count,
-                                                     double& ek, double& ep, unsigned long long& cnt, int& cmax,
-                                                     int& cmin)
+__global__ void __launch_bounds__(kForceThreads, 4)
+   k_force_stream(DevParams P, const float4* __restrict__ s_pos4, const float4* __restrict__ s_posA4,
+                  const float4* __restrict__ s_velB4, const float* __restrict__ s_rho,
+                  const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ cell_start,
+                  const uint32_t* __restrict__ idx_sorted, const uint2* __restrict__ hit_rec,
+                  const unsigned* __restrict__ hit_info, float4* __restrict__ pos4, float4* __restrict__ vel4,
+                  float4* __restrict__ s_acc4, int* __restrict__ s_count, double* __restrict__ block_partials,
+                  StepScalars* scal)
 {
-   const int rounds = (L.ntargets + kTileThreads - 1) / kTileThreads;
-#pragma unroll 1
-   for (int round = 0; round < rounds; round++)
-   {
-      const int tnum = round * kTileThreads + threadIdx.x;
-      const bool active = tnum < L.ntargets;
-      Target T = locate_target(t, L, active ? tnum : 0);
-      const int self_off = (T.k + L.row_delta[T.hr0]) * 16;
-      const float4 pi = *reinterpret_cast<const float4*>(smemA + self_off);
-      const float4 vi = *reinterpret_cast<const float4*>(smemA + offB + self_off);
-      ForceI I = make_force_i(P, pi, vi, s_rho[T.k]);
-      Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
-      int count = 0;
-      const unsigned info = active ? hit_info[T.k] : 0u;
-      const bool scan = (info & 0xffu) == kNoStream;
-      const int nw = scan ? 0 : (int)(info & 0xffu);
-      const int nhits = scan ? 0 : (int)(info >> 8);
-      const uint2* rec = hit_rec + stream_base(T.k);
-      int w = 0;
-      unsigned m = 0;
-      int base = 0;
-      uint2 nxt = make_uint2(0u, 0u);
-      if (nw > 0)
-         nxt = __ldg(rec);
-      const int nmax = __reduce_max_sync(0xffffffffu, nhits);
-#pragma unroll 1
-      for (int it = 0; it < nmax; it++)
-      {
-         if (it < nhits)
-         {
-            if (m == 0u)
-            {
-               // next record (records with an empty mask are never stored); prefetch the one after
-               m = nxt.x;
-               base = (int)nxt.y;
-               w++;
-               if (w < nw)
-                  nxt = __ldg(rec + (size_t)w * 32);
-            }
-            int bit = __ffs((int)m) - 1;
-            m &= m - 1u;
-            int off = base + bit * 16;
-            float4 pj = *reinterpret_cast<const float4*>(smemA + off);
-            float4 vj = *reinterpret_cast<const float4*>(smemA + offB + off);
-            count += force_candidate<UNIT_SCALE>(P, I, pj, vj, off != self_off, pg, vt);
-         }
-      }
-      if (scan && active)   // record capacity exceeded in the density sweep: scan the staged runs instead
-         count = force_scan_target<UNIT_SCALE, true>(P, t, L, T, I, reinterpret_cast<const float4*>(smemA),
-                                                    reinterpret_cast<const float4*>(smemA + offB), pg, vt);
-      if (active)
-      {
-         double e1, e2;
-         force_store(P, T.k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, e1, e2);
-         ek += e1;
-         ep += e2;
-         cnt += (unsigned long long)count;
-         cmax = max(cmax, count);
-         cmin = min(cmin, count);
-      }
-   }
-}
-
-template <bool UNIT_SCALE>
-__global__ void __launch_bounds__(kTileThreads)
-   k_force_tiled(DevParams P, const float4* __restrict__ s_pos4, const float4* __restrict__ s_posA4,
-                 const float4* __restrict__ s_velB4, const float* __restrict__ s_rho,
-                 const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ idx_sorted,
-                 const uint2* __restrict__ hit_rec, const unsigned* __restrict__ hit_info,
-                 float4* __restrict__ pos4, float4* __restrict__ vel4, float4* __restrict__ s_acc4,
-                 int* __restrict__ s_count, double* __restrict__ block_partials, StepScalars* scal)
-{
-   extern __shared__ __align__(16) unsigned char smem_raw[];
-   float4* spA = reinterpret_cast<float4*>(smem_raw);
-   float4* svB = spA + kCap;
-   __shared__ TileLayout L;
-   __shared__ int s_level, s_pop;
-   int X0, Y0, Z0;
-   tile_origin(P, X0, Y0, Z0);
-   if (threadIdx.x < 32)
-   {
-      int pop = tile_population(P, X0, Y0, Z0, cell_start);
-      int level = pop > 0 ? choose_level(P, X0, Y0, Z0, cell_start, kCap) : 0;
-      if (threadIdx.x == 0)
-      {
-         s_pop = pop;
-         s_level = level;
-      }
-   }
-   __syncthreads();
-   if (s_pop == 0)
-      return;   // block_partials were zeroed by the host for this step
+   __shared__ unsigned rmask_all[RSM * kForceThreads];
+   __shared__ unsigned rbase_all[RSM * kForceThreads];
+   unsigned* rmask = rmask_all + threadIdx.x;
+   unsigned* rbase = rbase_all + threadIdx.x;
+   const int k = blockIdx.x * kForceThreads + threadIdx.x;
+   const bool active = k < P.n;
+   const int kk = active ? k : 0;
    double ek = 0.0, ep = 0.0;
    unsigned long long cnt = 0;
    int cmax = -1, cmin = 0x7fffffff;
-   const int level = s_level;
-   const int bz = (level >= 1 && level < 4) ? TB / 2 : TB;
-   const int by = (level >= 2 && level < 4) ? TB / 2 : TB;
-   const int bx = (level >= 3 && level < 4) ? TB / 2 : TB;
-   for (int z = 0; z < TB; z += bz)
-      for (int y = 0; y < TB; y += by)
-         for (int x = 0; x < TB; x += bx)
+   // per-particle operands and the records: independent loads, issued together
+   const unsigned info = active ? hit_info[kk] : 0u;
+   const float4 pi = s_posA4[kk];
+   const float4 vi = s_velB4[kk];
+   const float rho_i = s_rho[kk];
+   const bool scan = (info & 0xffu) == kNoStream;
+   const int nw = scan ? 0 : (int)(info & 0xffu);
+   const int nhits = scan ? 0 : (int)(info >> 8);
+   const uint2* rec = hit_rec + stream_base(kk);
+#pragma unroll 4
+   for (int w = 0; w < min(nw, RSM); w++)
+   {
+      uint2 r2 = __ldg(rec + (size_t)w * 32);
+      rmask[w * kForceThreads] = r2.x;
+      rbase[w * kForceThreads] = r2.y;
+   }
+   ForceI I = make_force_i(P, pi, vi, rho_i);
+   Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
+   int count = 0;
+   int w = 0;
+   unsigned m = 0;
+   int base = 0;
+   // sorted index of this lane's next hit (records with an empty mask are never stored)
+   auto next_hit = [&]() -> int {
+      if (m == 0u)
+      {
+         if (w < RSM)
          {
-            SubTile t = {X0 + x, Y0 + y, Z0 + z, bx, by, bz};
-            setup_layout(P, t, cell_start, level < 4, L);
-            if (L.ntargets > 0 && level < 4)
-            {
-               stage_rows(t, L, s_posA4, spA);
-               stage_rows(t, L, s_velB4, svB);
-               __syncthreads();
-               force_targets_staged<UNIT_SCALE>(P, t, L, smem_raw, (int)(sizeof(float4) * kCap), s_pos4, s_rho,
-                                                idx_sorted, hit_rec, hit_info, pos4, vel4, s_acc4, s_count, ek, ep,
-                                                cnt, cmax, cmin);
-            }
-            else if (L.ntargets > 0)
-            {
-               // too dense to stage: same arithmetic straight from global memory
-               for (int tnum = threadIdx.x; tnum < L.ntargets; tnum += blockDim.x)
-               {
-                  Target T = locate_target(t, L, tnum);
-                  ForceI I = make_force_i(P, s_posA4[T.k], s_velB4[T.k], s_rho[T.k]);
-                  Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
-                  int count = force_scan_target<UNIT_SCALE, false>(P, t, L, T, I, s_posA4, s_velB4, pg, vt);
-                  double e1, e2;
-                  force_store(P, T.k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, e1, e2);
-                  ek += e1;
-                  ep += e2;
-                  cnt += (unsigned long long)count;
-                  cmax = max(cmax, count);
-                  cmin = min(cmin, count);
-               }
-            }
-            __syncthreads();
+            m = rmask[w * kForceThreads];
+            base = (int)rbase[w * kForceThreads];
          }
+         else
+         {
+            uint2 r2 = __ldg(rec + (size_t)w * 32);
+            m = r2.x;
+            base = (int)r2.y;
+         }
+         w++;
+      }
+      int lead = __clz((int)m);
+      m &= ~(0x80000000u >> lead);
+      return base + lead;
+   };
+   // two hits per trip: their gathers and arithmetic are independent (ILP); only the
+   // accumulation is ordered (the in-loop viscosity scaling, sph.cpp:880-882)
+   const int nmax = __reduce_max_sync(0xffffffffu, nhits);
+#pragma unroll 1
+   for (int it = 0; it < nmax; it += 2)
+   {
+      int j0 = kk, j1 = kk;
+      if (it < nhits)
+         j0 = next_hit();
+      if (it + 1 < nhits)
+         j1 = next_hit();
+      float4 pj0 = __ldg(&s_posA4[j0]);
+      float4 vj0 = __ldg(&s_velB4[j0]);
+      float4 pj1 = __ldg(&s_posA4[j1]);
+      float4 vj1 = __ldg(&s_velB4[j1]);
+      PairTerm t0 = force_term<UNIT_SCALE>(P, I, pj0, vj0, j0 != kk);
+      PairTerm t1 = force_term<UNIT_SCALE>(P, I, pj1, vj1, j1 != kk);
+      force_accumulate(I, t0, pg, vt, count);
+      force_accumulate(I, t1, pg, vt, count);
+   }
+   if (scan && active)
+   {
+      int b[9], e[9];
+      global_runs(P, keys_sorted[k], cell_start, b, e);
+#pragma unroll 1
+      for (int r = 0; r < 9; r++)
+         for (int j = b[r]; j < e[r]; j++)
+            count += force_candidate<UNIT_SCALE>(P, I, __ldg(&s_posA4[j]), __ldg(&s_velB4[j]), j != k, pg, vt);
+   }
+   if (active)
+   {
+      force_store(P, k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, ek, ep);
+      cnt = (unsigned long long)count;
+      cmax = count;
+      cmin = count;
+   }
    sph_block_reduce_scalars(ek, ep, cnt, cmax, cmin, block_partials, scal);
 }
 
@@ -825,7 +784,7 @@ __global__ void __launch_bounds__(kFlatThreads)
 }
 
 size_t density_smem() { return sizeof(float4) * (size_t)kCap; }
-size_t force_smem() { return sizeof(float4) * 2 * (size_t)kCap; }
+
 
 }  // namespace
 
@@ -833,10 +792,6 @@ int sph_full_configure(sphb200_ctx* ctx)
 {
    SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)density_smem()));
-   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_force_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)force_smem()));
-   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_force_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)force_smem()));
    // hit-mask stream: WCAP records per particle, interleaved per 32 sorted particles
    size_t groups = ((size_t)ctx->capacity + 31) / 32;
    SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->hit_rec, sizeof(uint2) * (groups ? groups : 1) * WCAP * 32));
@@ -868,39 +823,30 @@ int sph_step_full(sphb200_ctx* ctx)
    if (n == 0)
       return SPHB200_OK;
    const bool tiled = ctx->params.kernel_variant != 1;
-   int blocks;
    if (tiled)
    {
-      blocks = sph_full_tile_count(ctx);
-      SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_block_partials, 0, sizeof(double) * 2 * (size_t)blocks, st));
-      k_density_tiled<<<blocks, kTileThreads, density_smem(), st>>>(P, ctx->s_pos4, ctx->cell_start,
-                                                                   ctx->idx_sorted, ctx->vel4, ctx->s_posA4,
-                                                                   ctx->s_velB4, ctx->s_rho, ctx->hit_rec,
-                                                                   ctx->hit_info);
-      if (timed) cudaEventRecord(ctx->ev[3], st);
-      if (timed) cudaEventRecord(ctx->ev[4], st);
-      if (P.scale == 1.0f)
-         k_force_tiled<true><<<blocks, kTileThreads, force_smem(), st>>>(
-            P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->cell_start, ctx->idx_sorted, ctx->hit_rec,
-            ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials, ctx->d_scalars);
-      else
-         k_force_tiled<false><<<blocks, kTileThreads, force_smem(), st>>>(
-            P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->cell_start, ctx->idx_sorted, ctx->hit_rec,
-            ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials, ctx->d_scalars);
+      int tiles = sph_full_tile_count(ctx);
+      k_density_tiled<<<tiles, kTileThreads, density_smem(), st>>>(P, ctx->s_pos4, ctx->cell_start, ctx->idx_sorted,
+                                                                  ctx->vel4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
+                                                                  ctx->hit_rec, ctx->hit_info);
    }
    else
-   {
-      blocks = (n + kFlatThreads - 1) / kFlatThreads;
-      k_density_flat<<<blocks, kFlatThreads, 0, st>>>(P, ctx->s_pos4, ctx->keys_sorted, ctx->cell_start,
-                                                      ctx->idx_sorted, ctx->vel4, ctx->s_posA4, ctx->s_velB4,
-                                                      ctx->s_rho);
-      if (timed) cudaEventRecord(ctx->ev[3], st);
-      if (timed) cudaEventRecord(ctx->ev[4], st);
-      k_force_flat<<<blocks, kFlatThreads, 0, st>>>(P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
-                                                    ctx->keys_sorted, ctx->cell_start, ctx->idx_sorted, ctx->pos4,
-                                                    ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
-                                                    ctx->d_scalars);
-   }
+      k_density_flat<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, st>>>(
+         P, ctx->s_pos4, ctx->keys_sorted, ctx->cell_start, ctx->idx_sorted, ctx->vel4, ctx->s_posA4, ctx->s_velB4,
+         ctx->s_rho, ctx->hit_info);
+   if (timed) cudaEventRecord(ctx->ev[3], st);
+   if (timed) cudaEventRecord(ctx->ev[4], st);
+   const int blocks = (n + kForceThreads - 1) / kForceThreads;
+   if (P.scale == 1.0f)
+      k_force_stream<true><<<blocks, kForceThreads, 0, st>>>(
+         P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_sorted,
+         ctx->hit_rec, ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
+         ctx->d_scalars);
+   else
+      k_force_stream<false><<<blocks, kForceThreads, 0, st>>>(
+         P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_sorted,
+         ctx->hit_rec, ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
+         ctx->d_scalars);
    ctx->launches += 2;
    SPH_CUDA_CHECK(ctx, cudaGetLastError());
    if (timed) cudaEventRecord(ctx->ev[5], st);   // integrate is fused into the force sweep
