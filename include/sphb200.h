@@ -159,18 +159,35 @@ int sphb200_get_timings(sphb200_ctx* ctx, float ms[6]);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int sphb200_get_launch_count(const sphb200_ctx* ctx, long long* launches);
 
-/* ---- multi-GPU slabs along z (net-new) ------------------------- */
-/* 128-byte NCCL unique id for bootstrap through the caller's own channel */
+/* ---- multi-GPU slabs along z (net-new) -------------------------
+ * One context per GPU owns the voxel layers [z0, z1) of the GLOBAL grid given in
+ * SphParams (grid_z = whole box); particle_count is the slab's slot CAPACITY
+ * (owned + ghost particles + headroom for migration).  FULL neighbour mode only.
+ * In a slab context sphb200_step() first exchanges migrants and the ghost layer
+ * with the z-neighbours (one grouped ncclSend/ncclRecv pair each) and then runs
+ * the local step. */
+/* 128-byte NCCL unique id (rank 0 makes it, the caller broadcasts it through its
+ * own channel, e.g. torch.distributed) */
 int sphb200_comm_unique_id(void* id128);
-/* this context becomes slab `rank` of `nranks` (owns voxel layers
- * [z0, z1) of the global grid); particle_count is the slab CAPACITY */
+/* id128 == NULL makes a "virtual rank" without a communicator: several slabs in
+ * one process (even on one GPU) exchanged through sphb200_slab_transfer */
 int sphb200_comm_init(sphb200_ctx* ctx, int rank, int nranks, const void* id128, int z0, int z1);
 int sphb200_get_local_count(const sphb200_ctx* ctx, int* owned, int* ghosts);
-/* upload `count` owned particles with their global ids (slab mode) */
+/* `count` owned particles with their global ids; the remaining slots are free */
 int sphb200_upload_slab(sphb200_ctx* ctx, int count, const float* pos_xyz, const float* vel_xyz,
                         const float* mass, const uint32_t* global_ids);
+/* owned particles only, compacted, with their global ids (any order).  Fields:
+ * POSITION, VELOCITY, MASS, DENSITY, ACCELERATION, NEIGHBOR_COUNT */
 int sphb200_download_slab(sphb200_ctx* ctx, int field, void* dst, size_t dst_bytes, uint32_t* global_ids,
                           int* count);
+/* the phases of the exchange, for virtual ranks: pack on every slab, transfer each
+ * message to the neighbour (dir 0 = to rank-1, 1 = to rank+1), unpack, step_local */
+int sphb200_slab_pack(sphb200_ctx* ctx);
+int sphb200_slab_transfer(sphb200_ctx* src, int dir, sphb200_ctx* dst);
+int sphb200_slab_unpack(sphb200_ctx* ctx);
+int sphb200_slab_step_local(sphb200_ctx* ctx);
+/* SPHB200_E_CAPACITY when a halo message or the slot capacity overflowed */
+int sphb200_slab_status(sphb200_ctx* ctx);
 
 #ifdef __cplusplus
 }

@@ -8,6 +8,6 @@ contains no compute and no CPU fallback -- without the built library or without
 a CUDA device every entry point raises.
 """
 from .binding import (  # noqa: F401
-    FULL, SAMPLED, SPH, Field, SphDerived, SphError, SphParams, default_params, derive, lib, lib_path,
-    scene_lattice, scene_sphere,
+    FULL, SAMPLED, SPH, Field, SlabSPH, SphDerived, SphError, SphParams, default_params, derive, lib, lib_path,
+    scene_lattice, scene_sphere, slab_layers, step_virtual_slabs, voxel_layer,
 )

@@ -91,6 +91,11 @@ API = [
     ("sphb200_get_local_count", [_VP, C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
     ("sphb200_upload_slab", [_VP, C.c_int, _VP, _VP, _VP, _VP], C.c_int),
     ("sphb200_download_slab", [_VP, C.c_int, _VP, C.c_size_t, _VP, C.POINTER(C.c_int)], C.c_int),
+    ("sphb200_slab_pack", [_VP], C.c_int),
+    ("sphb200_slab_transfer", [_VP, C.c_int, _VP], C.c_int),
+    ("sphb200_slab_unpack", [_VP], C.c_int),
+    ("sphb200_slab_step_local", [_VP], C.c_int),
+    ("sphb200_slab_status", [_VP], C.c_int),
 ]
 
 
@@ -385,3 +390,100 @@ class SPH:
 
     def setCflLimit(self, v):
         self.set_params(cfl_limit=v)
+
+
+def slab_layers(grid_z, nranks, boundaries=None):
+    """Voxel-layer ranges [z0, z1) of `nranks` z-slabs tiling [0, grid_z).
+    Equal thickness unless explicit interior `boundaries` are given."""
+    if boundaries is None:
+        boundaries = [(grid_z * r) // nranks for r in range(1, nranks)]
+    edges = [0] + list(boundaries) + [grid_z]
+    assert len(edges) == nranks + 1 and all(b > a for a, b in zip(edges, edges[1:])), edges
+    return [(edges[r], edges[r + 1]) for r in range(nranks)]
+
+
+def voxel_layer(pos_z, h_times2_inv, grid_z):
+    """Global voxel layer of a z coordinate, as voxelizeParticles computes it
+    (sph.cpp:452-463): one f32 multiply, floor, clamp.  Host-side slab assignment."""
+    v = np.floor(np.asarray(pos_z, np.float32) * np.float32(h_times2_inv))
+    v = np.where(np.isfinite(v), v, -2147483648.0)
+    return np.clip(v, 0, grid_z - 1).astype(np.int64)
+
+
+class SlabSPH(SPH):
+    """One z-slab of a multi-GPU run (one per rank / GPU).  `params.grid_z` is the
+    GLOBAL grid and `params.particle_count` the slot capacity of this slab."""
+
+    def __init__(self, params, rank, nranks, z0, z1, nccl_id=None, device=-1):
+        super().__init__(params, device=device, init_scene=False)
+        self.rank, self.nranks, self.z0, self.z1 = rank, nranks, z0, z1
+        idbuf = None
+        if nccl_id is not None:
+            idbuf = (C.c_ubyte * 128).from_buffer_copy(bytes(nccl_id))
+        self._check(self._lib.sphb200_comm_init(self._h, rank, nranks, idbuf, z0, z1))
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_ubyte * 128)()
+        rc = lib().sphb200_comm_unique_id(buf)
+        if rc:
+            raise SphError(rc, lib().sphb200_last_error(None).decode())
+        return bytes(buf)
+
+    def upload_slab(self, pos, vel, mass, gids):
+        pos = np.ascontiguousarray(pos, np.float32).reshape(-1)
+        vel = np.ascontiguousarray(vel, np.float32).reshape(-1)
+        gids = np.ascontiguousarray(gids, np.uint32).reshape(-1)
+        n = gids.size
+        assert pos.size == 3 * n and vel.size == 3 * n
+        if mass is not None:
+            mass = np.ascontiguousarray(mass, np.float32).reshape(-1)
+        self._check(self._lib.sphb200_upload_slab(self._h, n, _ptr(pos), _ptr(vel), _ptr(mass), _ptr(gids)))
+
+    def download_slab(self, field):
+        cap = self.params.particle_count
+        comps, dt = {Field.POSITION: (3, np.float32), Field.VELOCITY: (3, np.float32), Field.MASS: (1, np.float32),
+                     Field.DENSITY: (1, np.float32), Field.ACCELERATION: (3, np.float32),
+                     Field.NEIGHBOR_COUNT: (1, np.int32)}[field]
+        out = np.empty((cap, comps), dt)
+        gids = np.empty(cap, np.uint32)
+        cnt = C.c_int()
+        self._check(self._lib.sphb200_download_slab(self._h, field, _ptr(out), out.nbytes, _ptr(gids), C.byref(cnt)))
+        out = out[:cnt.value]
+        return (out if comps > 1 else out[:, 0]), gids[:cnt.value]
+
+    def local_count(self):
+        o, g = C.c_int(), C.c_int()
+        self._check(self._lib.sphb200_get_local_count(self._h, C.byref(o), C.byref(g)))
+        return o.value, g.value
+
+    def pack(self):
+        self._check(self._lib.sphb200_slab_pack(self._h))
+
+    def transfer_to(self, direction, other):
+        self._check(self._lib.sphb200_slab_transfer(self._h, direction, other._h))
+
+    def unpack(self):
+        self._check(self._lib.sphb200_slab_unpack(self._h))
+
+    def step_local(self):
+        self._check(self._lib.sphb200_slab_step_local(self._h))
+
+    def status(self):
+        self._check(self._lib.sphb200_slab_status(self._h))
+
+
+def step_virtual_slabs(slabs, n_steps=1):
+    """Steps a list of virtual-rank slabs (one process, any devices) in lockstep:
+    pack everywhere, move each message to its neighbour, unpack, local step."""
+    for _ in range(n_steps):
+        for s in slabs:
+            s.pack()
+        for r, s in enumerate(slabs):
+            if r > 0:
+                s.transfer_to(0, slabs[r - 1])
+            if r + 1 < len(slabs):
+                s.transfer_to(1, slabs[r + 1])
+        for s in slabs:
+            s.unpack()
+            s.step_local()

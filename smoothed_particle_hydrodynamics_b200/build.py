@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("build of libsphb200.so failed")
     if force or procs or _newer(LIB, objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
-                                                    "-Xcompiler", "-fPIC", "-cudart", "static"]
+                                                    "-Xcompiler", "-fPIC", "-cudart", "static", "-ldl"]
         subprocess.check_call(cmd)
     return LIB
 

@@ -168,8 +168,8 @@ DevParams sph_dev_params(const sphb200_ctx* ctx)
    P.softening = d.softening;
    P.gvx = p.gravity[0]; P.gvy = p.gravity[1]; P.gvz = p.gravity[2];
    P.max_x = d.max_x; P.max_y = d.max_y; P.max_z = d.max_z;
-   P.z_lo = -std::numeric_limits<float>::infinity();
-   P.z_hi = std::numeric_limits<float>::infinity();
+   if (ctx->comm)
+      sph_comm_dev_params(ctx, P);
    return P;
 }
 
@@ -260,8 +260,6 @@ int sphb200_create(const SphParams* p, int device, sphb200_ctx** out)
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->keys_sorted, n));
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->idx_iota, n));
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->idx_sorted, n));
-   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->cell_count, (size_t)ctx->cells_alloc + 1));
-   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->cell_start, (size_t)ctx->cells_alloc + 1));
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->s_posA4, n));   // also the upload / download staging
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->s_velB4, n));
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->stage_f, n));
@@ -314,7 +312,7 @@ int sphb200_destroy(sphb200_ctx* ctx)
       cudaStreamSynchronize(ctx->stream);
    sph_comm_free(ctx);
    void* bufs[] = {ctx->pos4, ctx->vel4, ctx->gid, ctx->keys, ctx->keys_sorted, ctx->idx_iota, ctx->idx_sorted,
-                   ctx->cell_count, ctx->cell_start, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
+                   ctx->cell_count, ctx->cell_start, ctx->slot_state, ctx->idx_fixed, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
                    ctx->s_acc4, ctx->s_count, ctx->nbr_idx, ctx->nbr_dist, ctx->nbr_count, ctx->rho, ctx->acc4,
                    ctx->voxel_id, ctx->vg_count, ctx->vg_start, ctx->vg_members, ctx->vg_keys, ctx->cub_temp,
                    ctx->d_scalars, ctx->d_block_partials, ctx->stage_f, ctx->hit_rec, ctx->hit_info};

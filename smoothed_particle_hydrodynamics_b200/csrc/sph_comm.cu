@@ -1,31 +1,681 @@
-// sph_comm.cu -- multi-GPU slab decomposition along z (placeholder stubs until
-// the halo / migration exchange lands; the symbols exist so the ABI is stable).
-#include "sph_internal.h"
+// sph_comm.cu -- multi-GPU slab decomposition along z (net-new; the reference is
+// single-process).
+//
+// One context = one rank = one GPU owning the voxel layers [z0, z1) of the global
+// grid.  z is the slowest index of computeVoxelId (sph.cpp:1151-1154), so a slab is
+// a contiguous key range and local keys are global keys minus an offset.  The local
+// grid also carries one ghost voxel layer (width 2h) per neighbour: with 2h of
+// ghosts every particle within h of an owned particle has its own full
+// neighbourhood on this rank, so its density (needed at sph.cpp:829-830) is
+// recomputed locally and ONE exchange per step suffices.
+//
+// Storage is slot based: every slot of the particle arrays is OWNED, GHOST or FREE.
+// FREE slots get a sentinel cell key and fall behind all particles in the sort, so
+// nothing is ever compacted and the live count is read from the cell table on the
+// device (no host round trip per step).  Per step and per neighbour one message
+// {header, migrants, ghost layer} of fixed capacity goes out and one comes in --
+// a single grouped ncclSend/ncclRecv pair over NVLink.  Particles carry their
+// global id; the in-cell order is re-ranked by it (sph_grid.cu) so an N-slab run
+// reproduces the 1-slab run.
+//
+// Exchange rules for an OWNED particle whose voxel layer is now vz:
+//   vz >= z1 : migrant to rank+1; kept here as a GHOST when vz == z1 (it sits in the
+//              neighbour's boundary layer, which this rank needs as ghost anyway)
+//   vz <  z0 : symmetric, to rank-1
+//   otherwise: stays; copied into the neighbour's ghost message when vz is the
+//              first / last owned layer.
+// Old GHOST slots are dropped every step.  A particle that crosses more than one
+// slab in a step is forwarded one rank per step.
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is bound at run time, see NcclApi
+#include <stdlib.h>
+#include <string.h>
 
-int sph_comm_exchange(sphb200_ctx* ctx) { return sph_fail(ctx, SPHB200_E_COMM, "slab exchange not initialised"); }
-void sph_comm_free(sphb200_ctx*) {}
+#include <vector>
+
+#include "sph_math.cuh"
+
+struct SlabMsgHeader
+{
+   unsigned n_migrants, n_ghosts, pad0, pad1;
+};
+
+struct SlabEntry      // 32 bytes per particle on the wire
+{
+   float4 pos;        // x, y, z, mass
+   float4 vel;        // vx, vy, vz, global id (bits)
+};
+
+struct SlabComm
+{
+   ncclComm_t nccl;
+   bool has_nccl;
+   int rank, nranks;
+   int z0, z1;            // owned voxel layers
+   int zlo, zhi;          // local grid [zlo, zhi) = owned + ghost layers
+   int mig_cap, ghost_cap;
+   size_t msg_bytes;
+   unsigned char* send[2];   // 0: to rank-1 (down), 1: to rank+1 (up)
+   unsigned char* recv[2];   // 0: from rank-1,      1: from rank+1
+   uint32_t* free_list;      // FREE slot indices of this step
+   unsigned* counters;       // [0] n_free, [1] overflow flag
+   unsigned h_counters[2];
+};
+
+namespace
+{
+
+// NCCL is bound with dlopen at the first use instead of at link time: a process
+// that also imports torch must end up with ONE libnccl.so.2 (torch bundles a newer
+// one than the system's), whichever of the two libraries is loaded first.
+struct NcclApi
+{
+   ncclResult_t (*GetUniqueId)(ncclUniqueId*);
+   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
+   ncclResult_t (*CommDestroy)(ncclComm_t);
+   ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+   ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+   ncclResult_t (*GroupStart)();
+   ncclResult_t (*GroupEnd)();
+   const char* (*GetErrorString)(ncclResult_t);
+   bool ok;
+   std::string why;
+};
+
+NcclApi& nccl_api()
+{
+   static NcclApi api = [] {
+      NcclApi a;
+      memset(&a, 0, offsetof(NcclApi, ok));
+      a.ok = false;
+      void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);   // already in the process (torch)?
+      if (!h)
+         if (const char* env = getenv("SPHB200_NCCL_LIB"))
+            h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+      if (!h)
+         h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+      if (!h)
+      {
+         a.why = std::string("cannot load libnccl.so.2: ") + dlerror();
+         return a;
+      }
+      *(void**)&a.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+      *(void**)&a.CommInitRank = dlsym(h, "ncclCommInitRank");
+      *(void**)&a.CommDestroy = dlsym(h, "ncclCommDestroy");
+      *(void**)&a.Send = dlsym(h, "ncclSend");
+      *(void**)&a.Recv = dlsym(h, "ncclRecv");
+      *(void**)&a.GroupStart = dlsym(h, "ncclGroupStart");
+      *(void**)&a.GroupEnd = dlsym(h, "ncclGroupEnd");
+      *(void**)&a.GetErrorString = dlsym(h, "ncclGetErrorString");
+      a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.GroupStart && a.GroupEnd &&
+             a.GetErrorString;
+      if (!a.ok)
+         a.why = "libnccl.so.2 lacks a required symbol";
+      return a;
+   }();
+   return api;
+}
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ SlabEntry* msg_entries(unsigned char* msg)
+{
+   return reinterpret_cast<SlabEntry*>(msg + sizeof(SlabMsgHeader));
+}
+
+// classify every slot, build this step's outgoing messages and the free list
+__global__ void __launch_bounds__(kThreads)
+   k_slab_pack(DevParams P, int capacity, int z0, int z1, int has_down, int has_up, int mig_cap, int ghost_cap,
+               const float4* __restrict__ pos4, const float4* __restrict__ vel4, const uint32_t* __restrict__ gid,
+               unsigned char* __restrict__ state, unsigned char* __restrict__ msg_down,
+               unsigned char* __restrict__ msg_up, uint32_t* __restrict__ free_list, unsigned* __restrict__ counters)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= capacity)
+      return;
+   unsigned char st = state[i];
+   if (st != SLOT_OWNED)
+   {
+      // FREE stays free; last step's ghosts are dropped (fresh ones arrive below)
+      state[i] = SLOT_FREE;
+      free_list[atomicAdd(&counters[0], 1u)] = (uint32_t)i;
+      return;
+   }
+   float4 p = pos4[i];
+   int vz = sph_voxel_coord(p.z, P.h_times2_inv, P.gz_global);
+   int dir = -1;          // message this particle goes into: 0 down, 1 up
+   bool migrant = false;
+   if (vz >= z1 && has_up)
+   {
+      dir = 1;
+      migrant = true;
+   }
+   else if (vz < z0 && has_down)
+   {
+      dir = 0;
+      migrant = true;
+   }
+   else if (vz == z1 - 1 && has_up)
+      dir = 1;
+   bool also_down = !migrant && vz == z0 && has_down;   // 1-layer slabs ghost both ways
+   if (dir < 0 && !also_down)
+      return;
+   float4 v = vel4[i];
+   SlabEntry e;
+   e.pos = p;
+   e.vel = make_float4(v.x, v.y, v.z, __uint_as_float(gid[i]));
+   if (migrant)
+   {
+      unsigned char* msg = dir ? msg_up : msg_down;
+      SlabMsgHeader* hdr = reinterpret_cast<SlabMsgHeader*>(msg);
+      unsigned slot = atomicAdd(&hdr->n_migrants, 1u);
+      if (slot < (unsigned)mig_cap)
+         msg_entries(msg)[slot] = e;
+      else
+         atomicMax(&counters[1], 1u);
+      bool keep_ghost = dir ? (vz == z1) : (vz == z0 - 1);
+      if (keep_ghost)
+         state[i] = SLOT_GHOST;
+      else
+      {
+         state[i] = SLOT_FREE;
+         free_list[atomicAdd(&counters[0], 1u)] = (uint32_t)i;
+      }
+      return;
+   }
+   if (dir == 1)
+   {
+      SlabMsgHeader* hdr = reinterpret_cast<SlabMsgHeader*>(msg_up);
+      unsigned slot = atomicAdd(&hdr->n_ghosts, 1u);
+      if (slot < (unsigned)ghost_cap)
+         msg_entries(msg_up)[mig_cap + slot] = e;
+      else
+         atomicMax(&counters[1], 1u);
+   }
+   if (also_down)
+   {
+      SlabMsgHeader* hdr = reinterpret_cast<SlabMsgHeader*>(msg_down);
+      unsigned slot = atomicAdd(&hdr->n_ghosts, 1u);
+      if (slot < (unsigned)ghost_cap)
+         msg_entries(msg_down)[mig_cap + slot] = e;
+      else
+         atomicMax(&counters[1], 1u);
+   }
+}
+
+// arrivals of both incoming messages into free slots
+__global__ void __launch_bounds__(kThreads)
+   k_slab_unpack(int mig_cap, int ghost_cap, const unsigned char* __restrict__ msg_down,
+                 const unsigned char* __restrict__ msg_up, const uint32_t* __restrict__ free_list,
+                 unsigned* __restrict__ counters, float4* __restrict__ pos4, float4* __restrict__ vel4,
+                 uint32_t* __restrict__ gid, unsigned char* __restrict__ state)
+{
+   const SlabMsgHeader hd = *reinterpret_cast<const SlabMsgHeader*>(msg_down);
+   const SlabMsgHeader hu = *reinterpret_cast<const SlabMsgHeader*>(msg_up);
+   unsigned c0 = min(hd.n_migrants, (unsigned)mig_cap), c1 = min(hd.n_ghosts, (unsigned)ghost_cap);
+   unsigned c2 = min(hu.n_migrants, (unsigned)mig_cap), c3 = min(hu.n_ghosts, (unsigned)ghost_cap);
+   unsigned total = c0 + c1 + c2 + c3;
+   unsigned a = blockIdx.x * blockDim.x + threadIdx.x;
+   if (a >= total)
+      return;
+   if (a >= counters[0])
+   {
+      atomicMax(&counters[1], 2u);   // out of free slots: particle capacity exceeded
+      return;
+   }
+   const SlabEntry* src;
+   unsigned char st;
+   if (a < c0)
+   {
+      src = msg_entries(const_cast<unsigned char*>(msg_down)) + a;
+      st = SLOT_OWNED;
+   }
+   else if (a < c0 + c1)
+   {
+      src = msg_entries(const_cast<unsigned char*>(msg_down)) + mig_cap + (a - c0);
+      st = SLOT_GHOST;
+   }
+   else if (a < c0 + c1 + c2)
+   {
+      src = msg_entries(const_cast<unsigned char*>(msg_up)) + (a - c0 - c1);
+      st = SLOT_OWNED;
+   }
+   else
+   {
+      src = msg_entries(const_cast<unsigned char*>(msg_up)) + mig_cap + (a - c0 - c1 - c2);
+      st = SLOT_GHOST;
+   }
+   SlabEntry e = *src;
+   uint32_t slot = free_list[a];
+   pos4[slot] = e.pos;
+   vel4[slot] = make_float4(e.vel.x, e.vel.y, e.vel.z, 0.0f);
+   gid[slot] = __float_as_uint(e.vel.w);
+   state[slot] = st;
+}
+
+__global__ void __launch_bounds__(kThreads)
+   k_slab_upload(int capacity, int count, const float* __restrict__ pos_xyz, const float* __restrict__ vel_xyz,
+                 const float* __restrict__ mass, const uint32_t* __restrict__ ids, float4* __restrict__ pos4,
+                 float4* __restrict__ vel4, uint32_t* __restrict__ gid, unsigned char* __restrict__ state)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= capacity)
+      return;
+   if (i < count)
+   {
+      pos4[i] = make_float4(pos_xyz[3 * (size_t)i], pos_xyz[3 * (size_t)i + 1], pos_xyz[3 * (size_t)i + 2],
+                            mass ? mass[i] : 1.0f);
+      vel4[i] = make_float4(vel_xyz[3 * (size_t)i], vel_xyz[3 * (size_t)i + 1], vel_xyz[3 * (size_t)i + 2], 0.0f);
+      gid[i] = ids[i];
+      state[i] = SLOT_OWNED;
+   }
+   else
+   {
+      pos4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vel4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      gid[i] = 0xffffffffu;
+      state[i] = SLOT_FREE;
+   }
+}
+
+int blocks_for(int n) { return (n + kThreads - 1) / kThreads; }
+
+#define SPH_NCCL_CHECK(ctx, expr)                                                                        \
+   do                                                                                                    \
+   {                                                                                                     \
+      ncclResult_t _r = (expr);                                                                          \
+      if (_r != ncclSuccess)                                                                             \
+         return sph_fail(ctx, SPHB200_E_COMM, std::string(#expr) + ": " + nccl_api().GetErrorString(_r)); \
+   } while (0)
+
+int require_slab(sphb200_ctx* ctx, const char* what)
+{
+   if (!ctx)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null context");
+   if (!ctx->comm)
+      return sph_fail(ctx, SPHB200_E_INVALID, std::string(what) + ": context is not a slab (call sphb200_comm_init)");
+   return SPHB200_OK;
+}
+
+}  // namespace
+
+void sph_comm_dev_params(const sphb200_ctx* ctx, DevParams& P)
+{
+   const SlabComm* c = ctx->comm;
+   P.slab = 1;
+   P.n = ctx->capacity;
+   P.gz_global = ctx->params.grid_z;
+   P.vz_offset = c->zlo;
+   P.gz = c->zhi - c->zlo;
+   P.fz = 2 * P.gz;
+   P.ghost_lo = c->z0 - c->zlo;
+   P.ghost_hi = c->zhi - c->z1;
+   P.slot_state = ctx->slot_state;
+   P.slot_gid = ctx->gid;
+   P.d_nlive = ctx->cell_start + ctx->cells_fine;
+}
+
+void sph_comm_free(sphb200_ctx* ctx)
+{
+   SlabComm* c = ctx->comm;
+   if (!c)
+      return;
+   if (c->has_nccl && c->nccl)
+      nccl_api().CommDestroy(c->nccl);
+   for (int d = 0; d < 2; d++)
+   {
+      if (c->send[d]) cudaFree(c->send[d]);
+      if (c->recv[d]) cudaFree(c->recv[d]);
+   }
+   if (c->free_list) cudaFree(c->free_list);
+   if (c->counters) cudaFree(c->counters);
+   if (ctx->gid) cudaFree(ctx->gid);
+   if (ctx->slot_state) cudaFree(ctx->slot_state);
+   if (ctx->idx_fixed) cudaFree(ctx->idx_fixed);
+   ctx->gid = nullptr;
+   ctx->slot_state = nullptr;
+   ctx->idx_fixed = nullptr;
+   delete c;
+   ctx->comm = nullptr;
+}
+
+// pack this step's outgoing messages (enqueued on the context's stream)
+static int slab_pack(sphb200_ctx* ctx)
+{
+   SlabComm* c = ctx->comm;
+   DevParams P = sph_dev_params(ctx);
+   cudaStream_t st = ctx->stream;
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->counters, 0, sizeof(unsigned) * 2, st));
+   for (int d = 0; d < 2; d++)
+      SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->send[d], 0, sizeof(SlabMsgHeader), st));
+   if (ctx->capacity > 0)
+   {
+      k_slab_pack<<<blocks_for(ctx->capacity), kThreads, 0, st>>>(
+         P, ctx->capacity, c->z0, c->z1, c->rank > 0, c->rank < c->nranks - 1, c->mig_cap, c->ghost_cap, ctx->pos4,
+         ctx->vel4, ctx->gid, ctx->slot_state, c->send[0], c->send[1], c->free_list, c->counters);
+      ctx->launches++;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   }
+   return SPHB200_OK;
+}
+
+static int slab_unpack(sphb200_ctx* ctx)
+{
+   SlabComm* c = ctx->comm;
+   int max_arrivals = 2 * (c->mig_cap + c->ghost_cap);
+   k_slab_unpack<<<blocks_for(max_arrivals), kThreads, 0, ctx->stream>>>(
+      c->mig_cap, c->ghost_cap, c->recv[0], c->recv[1], c->free_list, c->counters, ctx->pos4, ctx->vel4, ctx->gid,
+      ctx->slot_state);
+   ctx->launches++;
+   SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   ctx->voxel_ids_valid = false;
+   return SPHB200_OK;
+}
+
+// pack -> one grouped send/recv per neighbour over NCCL -> unpack
+int sph_comm_exchange(sphb200_ctx* ctx)
+{
+   SlabComm* c = ctx->comm;
+   if (!c->has_nccl)
+      return sph_fail(ctx, SPHB200_E_COMM,
+                      "step: this slab has no NCCL communicator (virtual rank): drive it with "
+                      "sphb200_slab_pack / _transfer / _unpack / _step_local");
+   int rc = slab_pack(ctx);
+   if (rc)
+      return rc;
+   cudaStream_t st = ctx->stream;
+   if (c->nranks > 1)
+   {
+      NcclApi& N = nccl_api();
+      SPH_NCCL_CHECK(ctx, N.GroupStart());
+      if (c->rank > 0)
+      {
+         SPH_NCCL_CHECK(ctx, N.Send(c->send[0], c->msg_bytes, ncclUint8, c->rank - 1, c->nccl, st));
+         SPH_NCCL_CHECK(ctx, N.Recv(c->recv[0], c->msg_bytes, ncclUint8, c->rank - 1, c->nccl, st));
+      }
+      if (c->rank < c->nranks - 1)
+      {
+         SPH_NCCL_CHECK(ctx, N.Send(c->send[1], c->msg_bytes, ncclUint8, c->rank + 1, c->nccl, st));
+         SPH_NCCL_CHECK(ctx, N.Recv(c->recv[1], c->msg_bytes, ncclUint8, c->rank + 1, c->nccl, st));
+      }
+      SPH_NCCL_CHECK(ctx, N.GroupEnd());
+   }
+   return slab_unpack(ctx);
+}
 
 extern "C" {
 
-int sphb200_comm_unique_id(void*) { return sph_fail(nullptr, SPHB200_E_COMM, "slab mode not built yet"); }
-int sphb200_comm_init(sphb200_ctx* ctx, int, int, const void*, int, int)
+int sphb200_comm_unique_id(void* id128)
 {
-   return sph_fail(ctx, SPHB200_E_COMM, "slab mode not built yet");
+   if (!id128)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null id buffer");
+   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+   NcclApi& N = nccl_api();
+   if (!N.ok)
+      return sph_fail(nullptr, SPHB200_E_COMM, N.why);
+   ncclUniqueId id;
+   ncclResult_t r = N.GetUniqueId(&id);
+   if (r != ncclSuccess)
+      return sph_fail(nullptr, SPHB200_E_COMM, std::string("ncclGetUniqueId: ") + N.GetErrorString(r));
+   memcpy(id128, &id, 128);
+   return SPHB200_OK;
 }
+
+int sphb200_comm_init(sphb200_ctx* ctx, int rank, int nranks, const void* id128, int z0, int z1)
+{
+   if (!ctx)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null context");
+   if (ctx->comm)
+      return sph_fail(ctx, SPHB200_E_INVALID, "comm_init: already a slab");
+   if (ctx->params.neighbor_mode != SPHB200_NEIGHBORS_FULL)
+      return sph_fail(ctx, SPHB200_E_INVALID, "comm_init: slab decomposition needs neighbor_mode FULL");
+   const int gz = ctx->params.grid_z;
+   if (nranks < 1 || rank < 0 || rank >= nranks || z0 < 0 || z1 > gz || z1 - z0 < 1)
+      return sph_fail(ctx, SPHB200_E_INVALID, "comm_init: bad rank / layer range");
+   if ((rank == 0) != (z0 == 0) || (rank == nranks - 1) != (z1 == gz))
+      return sph_fail(ctx, SPHB200_E_INVALID, "comm_init: slabs must tile [0, grid_z) in rank order");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   SlabComm* c = new SlabComm();
+   memset(c, 0, sizeof(*c));
+   c->rank = rank;
+   c->nranks = nranks;
+   c->z0 = z0;
+   c->z1 = z1;
+   c->zlo = rank > 0 ? z0 - 1 : z0;
+   c->zhi = rank < nranks - 1 ? z1 + 1 : z1;
+   // one voxel layer of ghosts; 2.5x the mean layer population as headroom
+   long long per_layer = ((long long)ctx->capacity + (z1 - z0) - 1) / (z1 - z0);
+   long long gcap = per_layer * 5 / 2 + 1024;
+   if (const char* env = getenv("SPHB200_HALO_CAPACITY"))
+      gcap = atoll(env);
+   if (gcap > ctx->capacity)
+      gcap = ctx->capacity;
+   if (gcap < 1)
+      gcap = 1;
+   c->ghost_cap = (int)gcap;
+   c->mig_cap = (int)(gcap / 4 + 256);
+   c->msg_bytes = sizeof(SlabMsgHeader) + sizeof(SlabEntry) * ((size_t)c->ghost_cap + (size_t)c->mig_cap);
+   ctx->comm = c;
+   for (int d = 0; d < 2; d++)
+   {
+      SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->send[d], c->msg_bytes));
+      SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->recv[d], c->msg_bytes));
+      SPH_CUDA_CHECK(ctx, cudaMemset(c->send[d], 0, sizeof(SlabMsgHeader)));
+      SPH_CUDA_CHECK(ctx, cudaMemset(c->recv[d], 0, sizeof(SlabMsgHeader)));
+   }
+   const size_t cap = (size_t)(ctx->capacity > 0 ? ctx->capacity : 1);
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->free_list, sizeof(uint32_t) * cap));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->counters, sizeof(unsigned) * 2));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->gid, sizeof(uint32_t) * cap));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->slot_state, cap));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->idx_fixed, sizeof(uint32_t) * cap));
+   SPH_CUDA_CHECK(ctx, cudaMemset(ctx->slot_state, SLOT_FREE, cap));
+   SPH_CUDA_CHECK(ctx, cudaMemset(ctx->gid, 0xff, sizeof(uint32_t) * cap));
+   // cell tables for the LOCAL grid
+   sph_grid_free(ctx);
+   ctx->cells_voxel = ctx->params.grid_x * ctx->params.grid_y * (c->zhi - c->zlo);
+   ctx->cells_fine = 8 * ctx->cells_voxel;
+   ctx->cells_alloc = ctx->cells_fine;
+   int rc = sph_grid_alloc(ctx);
+   if (rc)
+      return rc;
+   ctx->n_local = ctx->capacity;
+   ctx->n_owned = 0;
+   if (id128 && nranks > 1)
+   {
+      NcclApi& N = nccl_api();
+      if (!N.ok)
+         return sph_fail(ctx, SPHB200_E_COMM, N.why);
+      ncclUniqueId id;
+      memcpy(&id, id128, 128);
+      SPH_NCCL_CHECK(ctx, N.CommInitRank(&c->nccl, nranks, id, rank));
+      c->has_nccl = true;
+   }
+   else if (nranks == 1)
+      c->has_nccl = true, c->nccl = nullptr;   // single slab: nothing to exchange
+   return SPHB200_OK;
+}
+
 int sphb200_get_local_count(const sphb200_ctx* ctx, int* owned, int* ghosts)
 {
    if (!ctx)
       return SPHB200_E_INVALID;
-   if (owned) *owned = ctx->n_owned;
-   if (ghosts) *ghosts = ctx->n_local - ctx->n_owned;
+   if (!ctx->comm)
+   {
+      if (owned) *owned = ctx->n_owned;
+      if (ghosts) *ghosts = 0;
+      return SPHB200_OK;
+   }
+   sphb200_ctx* c = const_cast<sphb200_ctx*>(ctx);
+   cudaSetDevice(ctx->device);
+   std::vector<unsigned char> st((size_t)ctx->capacity);
+   if (cudaMemcpyAsync(st.data(), ctx->slot_state, st.size(), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+       cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+      return sph_fail(c, SPHB200_E_CUDA, "get_local_count: copy failed");
+   int no = 0, ng = 0;
+   for (unsigned char s : st)
+   {
+      no += s == SLOT_OWNED;
+      ng += s == SLOT_GHOST;
+   }
+   if (owned) *owned = no;
+   if (ghosts) *ghosts = ng;
    return SPHB200_OK;
 }
-int sphb200_upload_slab(sphb200_ctx* ctx, int, const float*, const float*, const float*, const uint32_t*)
+
+int sphb200_upload_slab(sphb200_ctx* ctx, int count, const float* pos_xyz, const float* vel_xyz, const float* mass,
+                        const uint32_t* global_ids)
 {
-   return sph_fail(ctx, SPHB200_E_COMM, "slab mode not built yet");
+   int rc = require_slab(ctx, "upload_slab");
+   if (rc)
+      return rc;
+   if (count < 0 || count > ctx->capacity || (count > 0 && (!pos_xyz || !vel_xyz || !global_ids)))
+      return sph_fail(ctx, SPHB200_E_INVALID, "upload_slab: bad count or null argument");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   cudaStream_t st = ctx->stream;
+   float* d_pos = reinterpret_cast<float*>(ctx->s_posA4);
+   float* d_vel = reinterpret_cast<float*>(ctx->s_velB4);
+   uint32_t* d_ids = reinterpret_cast<uint32_t*>(ctx->keys);
+   if (count > 0)
+   {
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(d_pos, pos_xyz, sizeof(float) * 3 * (size_t)count, cudaMemcpyHostToDevice, st));
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(d_vel, vel_xyz, sizeof(float) * 3 * (size_t)count, cudaMemcpyHostToDevice, st));
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(d_ids, global_ids, sizeof(uint32_t) * (size_t)count, cudaMemcpyHostToDevice, st));
+      if (mass)
+         SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->stage_f, mass, sizeof(float) * (size_t)count, cudaMemcpyHostToDevice, st));
+   }
+   if (ctx->capacity > 0)
+   {
+      k_slab_upload<<<blocks_for(ctx->capacity), kThreads, 0, st>>>(ctx->capacity, count, d_pos, d_vel,
+                                                                    mass ? ctx->stage_f : nullptr, d_ids, ctx->pos4,
+                                                                    ctx->vel4, ctx->gid, ctx->slot_state);
+      ctx->launches++;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   }
+   ctx->n_owned = count;
+   ctx->lists_valid = false;
+   ctx->snapshot_valid = false;
+   ctx->voxel_ids_valid = false;
+   ctx->unsorted_valid = false;
+   ctx->stepped = false;
+   return SPHB200_OK;
 }
-int sphb200_download_slab(sphb200_ctx* ctx, int, void*, size_t, uint32_t*, int*)
+
+// OWNED particles of this slab, compacted on the host, with their global ids.
+// dst_bytes is the capacity of dst; *count receives the number of particles.
+int sphb200_download_slab(sphb200_ctx* ctx, int field, void* dst, size_t dst_bytes, uint32_t* global_ids, int* count)
 {
-   return sph_fail(ctx, SPHB200_E_COMM, "slab mode not built yet");
+   int rc = require_slab(ctx, "download_slab");
+   if (rc)
+      return rc;
+   if (!dst || !count)
+      return sph_fail(ctx, SPHB200_E_INVALID, "download_slab: null argument");
+   size_t per = 0;
+   switch (field)
+   {
+   case SPHB200_F_POSITION: case SPHB200_F_VELOCITY: case SPHB200_F_ACCELERATION: per = 12; break;
+   case SPHB200_F_MASS: case SPHB200_F_DENSITY: case SPHB200_F_NEIGHBOR_COUNT: per = 4; break;
+   default:
+      return sph_fail(ctx, SPHB200_E_INVALID, "download_slab: field not available per slab");
+   }
+   const size_t cap = (size_t)ctx->capacity;
+   std::vector<unsigned char> all(per * cap), st(cap);
+   std::vector<uint32_t> ids(cap);
+   const int n_save = ctx->n_local;
+   ctx->n_local = ctx->capacity;
+   rc = sphb200_download(ctx, field, all.data(), all.size());
+   ctx->n_local = n_save;
+   if (rc)
+      return rc;
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(st.data(), ctx->slot_state, cap, cudaMemcpyDeviceToHost, ctx->stream));
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(ids.data(), ctx->gid, sizeof(uint32_t) * cap, cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+   size_t n = 0;
+   for (size_t i = 0; i < cap; i++)
+      if (st[i] == SLOT_OWNED)
+      {
+         if ((n + 1) * per > dst_bytes)
+            return sph_fail(ctx, SPHB200_E_INVALID, "download_slab: destination too small");
+         memcpy(static_cast<unsigned char*>(dst) + n * per, all.data() + i * per, per);
+         if (global_ids)
+            global_ids[n] = ids[i];
+         n++;
+      }
+   *count = (int)n;
+   return SPHB200_OK;
 }
+
+// ---- explicit phases (virtual ranks on one GPU; also what sphb200_step does) ----
+int sphb200_slab_pack(sphb200_ctx* ctx)
+{
+   int rc = require_slab(ctx, "slab_pack");
+   if (rc)
+      return rc;
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   return slab_pack(ctx);
 }
+
+// copies src's outgoing message for direction `dir` (0 down, 1 up) into dst's matching
+// receive buffer: the NCCL send/recv pair, done as a device copy between two contexts
+// of one process (virtual ranks; contexts may sit on the same GPU)
+int sphb200_slab_transfer(sphb200_ctx* src, int dir, sphb200_ctx* dst)
+{
+   int rc = require_slab(src, "slab_transfer");
+   if (rc)
+      return rc;
+   rc = require_slab(dst, "slab_transfer");
+   if (rc)
+      return rc;
+   if (dir < 0 || dir > 1 || src->comm->msg_bytes != dst->comm->msg_bytes ||
+       dst->comm->rank != src->comm->rank + (dir ? 1 : -1))
+      return sph_fail(src, SPHB200_E_INVALID, "slab_transfer: contexts are not neighbours in that direction");
+   SPH_CUDA_CHECK(src, cudaStreamSynchronize(src->stream));
+   SPH_CUDA_CHECK(dst, cudaStreamSynchronize(dst->stream));   // dst may still be reading its last message
+   SPH_CUDA_CHECK(src, cudaMemcpy(dst->comm->recv[1 - dir], src->comm->send[dir], src->comm->msg_bytes,
+                                  cudaMemcpyDefault));
+   return SPHB200_OK;
+}
+
+int sphb200_slab_unpack(sphb200_ctx* ctx)
+{
+   int rc = require_slab(ctx, "slab_unpack");
+   if (rc)
+      return rc;
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   return slab_unpack(ctx);
+}
+
+// the local step of a slab whose exchange was driven through the explicit phases
+int sphb200_slab_step_local(sphb200_ctx* ctx)
+{
+   int rc = require_slab(ctx, "slab_step_local");
+   if (rc)
+      return rc;
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   rc = sph_step_full(ctx);
+   if (rc == SPHB200_OK)
+      ctx->stepped = true;
+   return rc;
+}
+
+// 0 = fine; otherwise SPHB200_E_CAPACITY with the reason (message or slot capacity)
+int sphb200_slab_status(sphb200_ctx* ctx)
+{
+   int rc = require_slab(ctx, "slab_status");
+   if (rc)
+      return rc;
+   SlabComm* c = ctx->comm;
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(unsigned) * 2, cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+   if (c->h_counters[1] == 1)
+      return sph_fail(ctx, SPHB200_E_CAPACITY, "slab exchange: halo message capacity exceeded "
+                                               "(raise SPHB200_HALO_CAPACITY)");
+   if (c->h_counters[1] == 2)
+      return sph_fail(ctx, SPHB200_E_CAPACITY, "slab exchange: no free particle slot left (raise particle_count)");
+   return SPHB200_OK;
+}
+
+}  // extern "C"

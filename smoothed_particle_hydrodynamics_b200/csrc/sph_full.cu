@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kFlatThreads)
                   float* __restrict__ s_rho, unsigned* __restrict__ hit_info)
 {
    int k = blockIdx.x * blockDim.x + threadIdx.x;
-   if (k >= P.n)
+   if (k >= sph_live_count(P))
       return;
    hit_info[k] = kNoStream;   // the force sweep scans for these particles
    float4 pi = s_pos4[k];
@@ -641,7 +641,14 @@ __global__ void __launch_bounds__(kForceThreads, 4)
    unsigned* rmask = rmask_all + threadIdx.x;
    unsigned* rbase = rbase_all + threadIdx.x;
    const int k = blockIdx.x * kForceThreads + threadIdx.x;
-   const bool active = k < P.n;
+   bool active = k < sph_live_count(P);
+   if (P.slab && active)
+   {
+      // ghost-layer particles only lend their density / velocity to owned neighbours;
+      // the rank that owns them integrates them
+      int cz = (int)(keys_sorted[k] / (uint32_t)(P.fx * P.fy));
+      active = cz >= 2 * P.ghost_lo && cz < P.fz - 2 * P.ghost_hi;
+   }
    const int kk = active ? k : 0;
    double ek = 0.0, ep = 0.0;
    unsigned long long cnt = 0;
@@ -770,12 +777,12 @@ __global__ void __launch_bounds__(kFlatThreads)
 
 // sorted per-particle outputs back to particle-index order (download only)
 __global__ void __launch_bounds__(kFlatThreads)
-   k_unsort(int n, const uint32_t* __restrict__ idx_sorted, const float* __restrict__ s_rho,
+   k_unsort(DevParams P, const uint32_t* __restrict__ idx_sorted, const float* __restrict__ s_rho,
             const float4* __restrict__ s_acc4, const int* __restrict__ s_count, float* __restrict__ rho,
             float4* __restrict__ acc4, int* __restrict__ nbr_count)
 {
    int k = blockIdx.x * blockDim.x + threadIdx.x;
-   if (k >= n)
+   if (k >= sph_live_count(P))
       return;
    uint32_t o = idx_sorted[k];
    rho[o] = s_rho[k];
@@ -825,26 +832,26 @@ int sph_step_full(sphb200_ctx* ctx)
    const bool tiled = ctx->params.kernel_variant != 1;
    if (tiled)
    {
-      int tiles = sph_full_tile_count(ctx);
-      k_density_tiled<<<tiles, kTileThreads, density_smem(), st>>>(P, ctx->s_pos4, ctx->cell_start, ctx->idx_sorted,
+      int tiles = ((P.fx + TB - 1) / TB) * ((P.fy + TB - 1) / TB) * ((P.fz + TB - 1) / TB);   // local grid
+      k_density_tiled<<<tiles, kTileThreads, density_smem(), st>>>(P, ctx->s_pos4, ctx->cell_start, ctx->idx_order,
                                                                   ctx->vel4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
                                                                   ctx->hit_rec, ctx->hit_info);
    }
    else
       k_density_flat<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, st>>>(
-         P, ctx->s_pos4, ctx->keys_sorted, ctx->cell_start, ctx->idx_sorted, ctx->vel4, ctx->s_posA4, ctx->s_velB4,
+         P, ctx->s_pos4, ctx->keys_sorted, ctx->cell_start, ctx->idx_order, ctx->vel4, ctx->s_posA4, ctx->s_velB4,
          ctx->s_rho, ctx->hit_info);
    if (timed) cudaEventRecord(ctx->ev[3], st);
    if (timed) cudaEventRecord(ctx->ev[4], st);
    const int blocks = (n + kForceThreads - 1) / kForceThreads;
    if (P.scale == 1.0f)
       k_force_stream<true><<<blocks, kForceThreads, 0, st>>>(
-         P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_sorted,
+         P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_order,
          ctx->hit_rec, ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
          ctx->d_scalars);
    else
       k_force_stream<false><<<blocks, kForceThreads, 0, st>>>(
-         P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_sorted,
+         P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_order,
          ctx->hit_rec, ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
          ctx->d_scalars);
    ctx->launches += 2;
@@ -866,7 +873,7 @@ int sph_full_unsort(sphb200_ctx* ctx)
    if (n == 0 || !ctx->snapshot_valid)
       return SPHB200_OK;
    k_unsort<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, ctx->stream>>>(
-      n, ctx->idx_sorted, ctx->s_rho, ctx->s_acc4, ctx->s_count, ctx->rho, ctx->acc4, ctx->nbr_count);
+      sph_dev_params(ctx), ctx->idx_order, ctx->s_rho, ctx->s_acc4, ctx->s_count, ctx->rho, ctx->acc4, ctx->nbr_count);
    ctx->launches++;
    SPH_CUDA_CHECK(ctx, cudaGetLastError());
    ctx->unsorted_valid = true;
@@ -882,7 +889,7 @@ int sph_full_build_lists(sphb200_ctx* ctx)
    if (n > 0)
    {
       k_build_lists<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, ctx->stream>>>(
-         P, ctx->s_pos4, ctx->keys_sorted, ctx->cell_start, ctx->idx_sorted, ctx->nbr_idx, ctx->nbr_dist,
+         P, ctx->s_pos4, ctx->keys_sorted, ctx->cell_start, ctx->idx_order, ctx->nbr_idx, ctx->nbr_dist,
          ctx->nbr_count, ctx->d_scalars);
       ctx->launches++;
       SPH_CUDA_CHECK(ctx, cudaGetLastError());

@@ -17,8 +17,11 @@ constexpr int kThreads = 256;
 // SAMPLED mode: key = voxel id (sph.cpp:443-473, 1151-1154).
 // FULL mode:    key = fine-cell id, fine = 2*voxel + (orientation > h) per axis
 //               (the octant rule of sph.cpp:504-515), x fastest.
+// Slab mode:    the z voxel is clamped against the GLOBAL box exactly like the
+//               reference, then shifted into the rank's local grid; FREE slots get
+//               the sentinel key `cells` and therefore sort behind every particle.
 template <bool FINE>
-__global__ void __launch_bounds__(kThreads) k_cell_keys(DevParams P, const float4* __restrict__ pos4,
+__global__ void __launch_bounds__(kThreads) k_cell_keys(DevParams P, int cells, const float4* __restrict__ pos4,
                                                          uint32_t* __restrict__ keys,
                                                          uint32_t* __restrict__ cell_count,
                                                          int* __restrict__ voxel_id_out)
@@ -26,23 +29,32 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(DevParams P, const float
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= P.n)
       return;
+   if (P.slab && P.slot_state[i] == SLOT_FREE)
+   {
+      keys[i] = (uint32_t)cells;
+      atomicAdd(&cell_count[cells], 1u);
+      return;
+   }
    float4 p = pos4[i];
    int vx = sph_voxel_coord(p.x, P.h_times2_inv, P.gx);
    int vy = sph_voxel_coord(p.y, P.h_times2_inv, P.gy);
-   int vz = sph_voxel_coord(p.z, P.h_times2_inv, P.gz);
+   int vz = sph_voxel_coord(p.z, P.h_times2_inv, P.slab ? P.gz_global : P.gz);
+   int lz = vz;
+   if (P.slab)
+      lz = min(max(vz - P.vz_offset, 0), P.gz - 1);   // only a particle that jumped >1 slab is clamped
    uint32_t key;
    if (FINE)
    {
       int cx = 2 * vx + sph_upper_half(p.x, vx, P.h_times2, P.h);
       int cy = 2 * vy + sph_upper_half(p.y, vy, P.h_times2, P.h);
-      int cz = 2 * vz + sph_upper_half(p.z, vz, P.h_times2, P.h);
+      int cz = 2 * lz + sph_upper_half(p.z, vz, P.h_times2, P.h);
       key = (uint32_t)((cz * P.fy + cy) * P.fx + cx);
    }
    else
-      key = (uint32_t)sph_voxel_id(vx, vy, vz, P.gx, P.gy);
+      key = (uint32_t)sph_voxel_id(vx, vy, lz, P.gx, P.gy);
    keys[i] = key;
    if (voxel_id_out)
-      voxel_id_out[i] = sph_voxel_id(vx, vy, vz, P.gx, P.gy);
+      voxel_id_out[i] = sph_voxel_id(vx, vy, vz, P.gx, P.gy);   // global voxel id, as the reference numbers it
    atomicAdd(&cell_count[key], 1u);
 }
 
@@ -54,13 +66,38 @@ __global__ void __launch_bounds__(kThreads) k_iota(uint32_t* a, int n)
 }
 
 // particles into cell order: one 16-byte gather per particle
-__global__ void __launch_bounds__(kThreads) k_gather_pos(int n, const uint32_t* __restrict__ idx_sorted,
+__global__ void __launch_bounds__(kThreads) k_gather_pos(DevParams P, const uint32_t* __restrict__ idx_sorted,
                                                           const float4* __restrict__ pos4,
                                                           float4* __restrict__ s_pos4)
 {
    int k = blockIdx.x * blockDim.x + threadIdx.x;
-   if (k < n)
+   if (k < sph_live_count(P))
       s_pos4[k] = __ldg(&pos4[idx_sorted[k]]);
+}
+
+// Slab mode: a rank's slot order is arbitrary (arrivals land in free slots), so
+// the stable sort alone does not give the canonical in-cell order.  Re-rank the
+// members of every cell by GLOBAL particle id (== the single-GPU particle index
+// == the reference's push_back order, sph.cpp:476-480).  One thread per cell;
+// cells hold ~10 particles, so a rank-by-counting pass is cheap.
+__global__ void __launch_bounds__(kThreads) k_fix_cell_order(int cells, const uint32_t* __restrict__ cell_start,
+                                                              const uint32_t* __restrict__ idx_sorted,
+                                                              const uint32_t* __restrict__ gid,
+                                                              uint32_t* __restrict__ idx_fixed)
+{
+   int c = blockIdx.x * blockDim.x + threadIdx.x;
+   if (c >= cells)
+      return;
+   int s = (int)cell_start[c], e = (int)cell_start[c + 1];
+   for (int a = s; a < e; a++)
+   {
+      uint32_t ia = idx_sorted[a];
+      uint32_t ga = gid[ia];
+      int rank = 0;
+      for (int b = s; b < e; b++)
+         rank += (gid[idx_sorted[b]] < ga) ? 1 : 0;
+      idx_fixed[s + rank] = ia;
+   }
 }
 
 __global__ void k_reset_scalars(StepScalars* s)
@@ -124,42 +161,53 @@ int sph_finish_scalars(sphb200_ctx* ctx, int blocks)
 }
 
 // keys -> histogram -> exclusive scan -> stable radix sort of (key, index) ->
-// (FULL) gather positions into cell order.
+// (slab) in-cell order by global id -> (FULL) gather positions into cell order.
+// Afterwards ctx->idx_order is the particle order every later kernel uses.
 int sph_bin_and_sort(sphb200_ctx* ctx, bool fine)
 {
    DevParams P = sph_dev_params(ctx);
-   const int n = ctx->n_local;
+   const int n = ctx->n_local;              // slab mode: the slot capacity
    const int cells = fine ? ctx->cells_fine : ctx->cells_voxel;
+   const int table = cells + 2;             // [cells] = live count, [cells+1] = slots (slab sentinel cell)
    cudaStream_t st = ctx->stream;
-   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->cell_count, 0, sizeof(uint32_t) * ((size_t)cells + 1), st));
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->cell_count, 0, sizeof(uint32_t) * (size_t)table, st));
    if (n > 0)
    {
       if (fine)
-         k_cell_keys<true><<<blocks_for(n), kThreads, 0, st>>>(P, ctx->pos4, ctx->keys, ctx->cell_count,
+         k_cell_keys<true><<<blocks_for(n), kThreads, 0, st>>>(P, cells, ctx->pos4, ctx->keys, ctx->cell_count,
                                                                ctx->voxel_id);
       else
-         k_cell_keys<false><<<blocks_for(n), kThreads, 0, st>>>(P, ctx->pos4, ctx->keys, ctx->cell_count,
+         k_cell_keys<false><<<blocks_for(n), kThreads, 0, st>>>(P, cells, ctx->pos4, ctx->keys, ctx->cell_count,
                                                                 ctx->voxel_id);
       ctx->launches++;
       SPH_CUDA_CHECK(ctx, cudaGetLastError());
       ctx->voxel_ids_valid = true;
    }
    size_t temp = ctx->cub_temp_bytes;
-   SPH_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_temp, temp, ctx->cell_count, ctx->cell_start,
-                                                     cells + 1, st));
+   SPH_CUDA_CHECK(ctx, cub::DeviceScan::ExclusiveSum(ctx->cub_temp, temp, ctx->cell_count, ctx->cell_start, table,
+                                                     st));
    ctx->launches += 2;
+   ctx->idx_order = ctx->idx_sorted;
    if (n > 0)
    {
       int bits = 1;
-      while (bits < 32 && (1ll << bits) < (long long)cells)
+      while (bits < 32 && (1ll << bits) < (long long)cells + (ctx->comm ? 1 : 0))
          bits++;
       temp = ctx->cub_temp_bytes;
       SPH_CUDA_CHECK(ctx, cub::DeviceRadixSort::SortPairs(ctx->cub_temp, temp, ctx->keys, ctx->keys_sorted,
                                                           ctx->idx_iota, ctx->idx_sorted, n, 0, bits, st));
       ctx->launches += 1 + 2 * ((bits + 7) / 8);
+      if (ctx->comm)
+      {
+         k_fix_cell_order<<<blocks_for(cells), kThreads, 0, st>>>(cells, ctx->cell_start, ctx->idx_sorted, ctx->gid,
+                                                                  ctx->idx_fixed);
+         ctx->launches++;
+         SPH_CUDA_CHECK(ctx, cudaGetLastError());
+         ctx->idx_order = ctx->idx_fixed;
+      }
       if (fine)
       {
-         k_gather_pos<<<blocks_for(n), kThreads, 0, st>>>(n, ctx->idx_sorted, ctx->pos4, ctx->s_pos4);
+         k_gather_pos<<<blocks_for(n), kThreads, 0, st>>>(P, ctx->idx_order, ctx->pos4, ctx->s_pos4);
          ctx->launches++;
          SPH_CUDA_CHECK(ctx, cudaGetLastError());
       }
@@ -167,15 +215,36 @@ int sph_bin_and_sort(sphb200_ctx* ctx, bool fine)
    return SPHB200_OK;
 }
 
-// scratch sizing + iota; called once from sphb200_create
-int sph_grid_setup(sphb200_ctx* ctx)
+// cell tables + CUB scratch for the current grid (re-done when a context becomes a slab)
+int sph_grid_alloc(sphb200_ctx* ctx)
 {
+   size_t table = (size_t)ctx->cells_alloc + 2;
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->cell_count, sizeof(uint32_t) * table));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->cell_start, sizeof(uint32_t) * table));
    size_t t_scan = 0, t_sort = 0;
-   cub::DeviceScan::ExclusiveSum(nullptr, t_scan, (uint32_t*)nullptr, (uint32_t*)nullptr, ctx->cells_alloc + 1);
+   cub::DeviceScan::ExclusiveSum(nullptr, t_scan, (uint32_t*)nullptr, (uint32_t*)nullptr, (int)table);
    cub::DeviceRadixSort::SortPairs(nullptr, t_sort, (uint32_t*)nullptr, (uint32_t*)nullptr, (uint32_t*)nullptr,
                                    (uint32_t*)nullptr, ctx->capacity > 0 ? ctx->capacity : 1, 0, 32);
    ctx->cub_temp_bytes = (t_scan > t_sort ? t_scan : t_sort) + 256;
    SPH_CUDA_CHECK(ctx, cudaMalloc(&ctx->cub_temp, ctx->cub_temp_bytes));
+   return SPHB200_OK;
+}
+
+void sph_grid_free(sphb200_ctx* ctx)
+{
+   if (ctx->cell_count) cudaFree(ctx->cell_count);
+   if (ctx->cell_start) cudaFree(ctx->cell_start);
+   if (ctx->cub_temp) cudaFree(ctx->cub_temp);
+   ctx->cell_count = ctx->cell_start = nullptr;
+   ctx->cub_temp = nullptr;
+}
+
+// scratch sizing + iota; called once from sphb200_create
+int sph_grid_setup(sphb200_ctx* ctx)
+{
+   int rc = sph_grid_alloc(ctx);
+   if (rc)
+      return rc;
    if (ctx->capacity > 0)
    {
       k_iota<<<blocks_for(ctx->capacity), kThreads, 0, ctx->stream>>>(ctx->idx_iota, ctx->capacity);

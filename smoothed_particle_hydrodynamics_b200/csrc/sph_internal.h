@@ -33,8 +33,24 @@ struct DevParams
    float softening;
    float gvx, gvy, gvz;   // uniform gravity
    float max_x, max_y, max_z;
-   float z_lo, z_hi;      // slab mode: owned z range in world units (else -inf/+inf)
+   // slab mode (one z-slab of the global grid per GPU; all zero / null otherwise)
+   int slab;              // 1: slots may be FREE, live count comes from the device cell table
+   int gz_global;         // voxel layers of the whole box (binning clamps against this, like the reference)
+   int vz_offset;         // first voxel layer of the local grid (global layer index)
+   int ghost_lo, ghost_hi;// ghost voxel layers present below / above the owned range (0 or 1)
+   const unsigned char* slot_state;   // per slot: SLOT_FREE / SLOT_OWNED / SLOT_GHOST
+   const uint32_t* slot_gid;          // per slot: global particle id
+   const uint32_t* d_nlive;           // live (non-FREE) particles = cell_start[cells]
 };
+
+enum { SLOT_FREE = 0, SLOT_OWNED = 1, SLOT_GHOST = 2 };
+
+// number of particles a kernel has to process: by value on a single GPU, read from
+// the cell table (no host round trip) in slab mode
+__device__ __forceinline__ int sph_live_count(const DevParams& P)
+{
+   return P.slab ? (int)*P.d_nlive : P.n;
+}
 
 struct StepScalars     // per-step reductions, one device struct
 {
@@ -64,10 +80,13 @@ struct sphb200_ctx
    // persistent state, original (upload) order: xyz+mass, vel+pad
    float4* pos4;
    float4* vel4;
-   uint32_t* gid;         // global ids (slab mode), else NULL
+   uint32_t* gid;         // slab mode: global id per slot, else NULL
+   unsigned char* slot_state;   // slab mode: SLOT_* per slot, else NULL
+   uint32_t* idx_fixed;   // slab mode: idx_sorted re-ordered by global id inside each cell
 
    // per-step scratch
    uint32_t *keys, *keys_sorted, *idx_iota, *idx_sorted;
+   const uint32_t* idx_order;   // particle order of the last binning: idx_sorted, or idx_fixed in slab mode
    uint32_t* cell_count;  // histogram, cells_alloc + 1
    uint32_t* cell_start;  // exclusive scan, cells_alloc + 1
    float4* s_pos4;        // sorted snapshot (x,y,z,m)
@@ -138,5 +157,8 @@ int sph_finish_scalars(sphb200_ctx* ctx, int blocks);
 // sph_comm.cu
 int sph_comm_exchange(sphb200_ctx* ctx);
 void sph_comm_free(sphb200_ctx* ctx);
+void sph_comm_dev_params(const sphb200_ctx* ctx, DevParams& P);
+int sph_grid_alloc(sphb200_ctx* ctx);
+void sph_grid_free(sphb200_ctx* ctx);
 
 #endif
