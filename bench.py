@@ -38,6 +38,7 @@ from oracle import scenes  # noqa: E402  (input synthesis only)
 
 ALG_BYTES_STEP = 240.0     # algorithmic bytes per particle-step (whole pipeline)
 ALG_BYTES_FORCE = 72.0     # force+integrate+collide sweep: R(16+16+4) + W(16+16) + R4
+ALG_BYTES_DENSITY = 20.0   # density+EOS sweep: R16 + W4
 NU = 40.0
 
 
@@ -110,6 +111,41 @@ def workload_spec(name):
 
 
 # ----------------------------------------------------------------------------
+def column_scene(world, rank, strong):
+    """Multi-GPU scene: ONE continuous jittered lattice column along z, 256x128 sites
+    in x,y and 512 z-sites per GPU (weak scaling, SURVEY config 4: 16.7M per GPU) or 512
+    z-sites in total (strong scaling, config 3), lifted 16 voxels off the floor and
+    centred in x.  The box is cut into z-slabs on voxel layers so that every rank
+    owns the same number of lattice planes (+-1).  Each rank generates only its own
+    particles (counter-based jitter) and keeps those whose voxel layer it owns."""
+    import smoothed_particle_hydrodynamics_b200 as S
+    nx, ny = 256, 128
+    nz = 512 if strong else 512 * world
+    d = scenes.lattice_spacing(0.1, NU)
+    vox = 0.2
+    oz = 3
+    origin = (49 * vox, 16 * vox, oz * vox)
+    extent = nz * float(d) / vox                       # column height in voxel layers
+    gz = int(np.ceil(oz + extent)) + 4
+    bounds = [int(round(oz + extent * r / world)) for r in range(1, world)]
+    layers = S.slab_layers(gz, world, bounds)
+    z0, z1 = layers[rank]
+    # lattice planes that can reach this slab (jitter is +-0.1 d): one plane of margin
+    zpos = lambda iz: (origin[2] + (iz + 0.5) * float(d)) / vox
+    planes = [iz for iz in range(nz) if z0 - 1 <= zpos(iz) < z1 + 1]
+    first, last = (planes[0], planes[-1] + 1) if planes else (0, 0)
+    first_id, count = first * nx * ny, (last - first) * nx * ny
+    pos = np.empty((count, 3), np.float32)
+    if count:
+        S.scene_lattice(nx, ny, nz, d, origin, first_id=first_id, count=count, out=pos)
+    inv2h = np.float32(1.0) / (np.float32(0.1) * np.float32(2.0))
+    vz = S.voxel_layer(pos[:, 2], inv2h, gz)
+    own = (vz >= z0) & (vz < z1)
+    gids = (np.arange(count, dtype=np.int64) + first_id)[own].astype(np.uint32)
+    return dict(grid=(160, 64, gz), layers=layers, pos=pos[own], gids=gids, total=nx * ny * nz,
+                sites=(nx, ny, nz))
+
+
 def run_ours(args):
     import torch
     import smoothed_particle_hydrodynamics_b200 as S
@@ -117,40 +153,93 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (one rank per GPU)")
     torch.cuda.set_device(local)
+    dist = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    name = args.workload or ("dambreak_16m" if world == 1 else "boxdrop_16m")
-    cfg, nx, ny, nz, d, origin = workload_spec(name)
-    n = nx * ny * nz
     sp = scenes.scene_params(nu=NU)
-    if world > 1:
-        raise SystemExit("multi-GPU slab mode: see bench_slab (not wired in this build)")
-    p = S.default_params(particle_count=n, grid=cfg["grid"], examine_count=96, neighbor_mode=S.FULL,
-                         use_uniform_gravity=1, use_wall_collision=1, rho0=sp["rho0"], stiffness=sp["stiffness"],
-                         viscosity=sp["viscosity"], central_mass=0.0, gravity=sp["gravity"],
-                         time_step=sp["time_step"])
-    sph = S.SPH(p, device=local, init_scene=False)
+    common = dict(examine_count=96, neighbor_mode=S.FULL, use_uniform_gravity=1, use_wall_collision=1,
+                  rho0=sp["rho0"], stiffness=sp["stiffness"], viscosity=sp["viscosity"], central_mass=0.0,
+                  gravity=sp["gravity"], time_step=sp["time_step"])
+    strong = args.scaling == "strong"
+    force_slab = world == 1 and args.force_slab
+    if world == 1 and not force_slab:
+        name = args.workload or "dambreak_16m"
+        cfg, nx, ny, nz, d, origin = workload_spec(name)
+        n = n_total = nx * ny * nz
+        grid = cfg["grid"]
+        sph = S.SPH(S.default_params(particle_count=n, grid=grid, **common), device=local, init_scene=False)
+        capacity = n
+        workload = ("%s: %dx%dx%d jittered lattice = %d particles, h=0.1, lattice spacing for ~%.0f neighbours "
+                    "(continuum), voxel grid %s, FULL neighbour mode, gravity+walls on"
+                    % (name, nx, ny, nz, n, NU, "x".join(map(str, grid))))
+    else:
+        sc = column_scene(world, rank, strong)
+        n = sc["gids"].size
+        n_total = sc["total"]
+        grid = sc["grid"]
+        z0, z1 = sc["layers"][rank]
+        capacity = int(n * 1.12) + 400000
+        nccl_id = None
+        if world > 1:
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(S.SlabSPH.unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            nccl_id = bytes(idt.cpu().numpy().tobytes())
+        sph = S.SlabSPH(S.default_params(particle_count=capacity, grid=grid, **common), rank, world, z0, z1,
+                        nccl_id=nccl_id, device=local)
+        name = "column_%s_%dgpu" % ("strong16m" if strong else "weak16m_per_gpu", world)
+        workload = ("%s: continuous %dx%dx%d jittered lattice column = %d particles (%s), z-slabs of voxel layers "
+                    "%s, one ghost voxel layer + migration per step over NCCL, h=0.1, voxel grid %s, FULL mode, "
+                    "gravity+walls on" % (name, *sc["sites"], n_total,
+                                          "16.7M per GPU" if not strong else "16.7M in total", sc["layers"],
+                                          "x".join(map(str, grid))))
     stream = torch.cuda.Stream()
     sph.set_stream(stream.cuda_stream)
 
     # synthetic scene in pinned host memory (the e2e leg copies from / to it every step)
-    pos_h = torch.empty((n, 3), dtype=torch.float32).pin_memory()
-    vel_h = torch.zeros((n, 3), dtype=torch.float32).pin_memory()
-    mass_h = torch.ones((n,), dtype=torch.float32).pin_memory()
-    S.scene_lattice(nx, ny, nz, d, origin, out=pos_h.numpy())
-    sph.upload_ptr(pos_h.data_ptr(), vel_h.data_ptr(), mass_h.data_ptr())
+    pos_h = torch.empty((capacity, 3), dtype=torch.float32).pin_memory()
+    vel_h = torch.zeros((capacity, 3), dtype=torch.float32).pin_memory()
+    mass_h = torch.ones((capacity,), dtype=torch.float32).pin_memory()
+    gid_h = torch.zeros((capacity,), dtype=torch.int32).pin_memory()
+
+    slab = world > 1 or force_slab
+
+    def load_scene():
+        vel_h.zero_()
+        if not slab:
+            S.scene_lattice(nx, ny, nz, d, origin, out=pos_h.numpy())
+            sph.upload_ptr(pos_h.data_ptr(), vel_h.data_ptr(), mass_h.data_ptr())
+        else:
+            pos_h.numpy()[:n] = sc["pos"]
+            gid_h.numpy()[:n] = sc["gids"].view(np.int32)
+            sph._check(sph._lib.sphb200_upload_slab(sph._h, n, pos_h.data_ptr(), vel_h.data_ptr(),
+                                                    mass_h.data_ptr(), gid_h.data_ptr()))
+    load_scene()
     sph.synchronize()
 
     def barrier():
         if world > 1:
-            import torch.distributed as dist
             dist.barrier()
         torch.cuda.synchronize()
+
+    def allmax(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
     # ---- device-resident throughput ----------------------------------------
     sampler = ClockSampler(local)
@@ -159,7 +248,6 @@ def run_ours(args):
     barrier()
     l0 = sph.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    pairs = 0
     barrier()
     t_begin = time.time()
     with torch.cuda.stream(stream):
@@ -168,17 +256,14 @@ def run_ours(args):
         e1.record(stream)
     barrier()
     t_end = time.time()
-    ms = e0.elapsed_time(e1)
+    ms = allmax(e0.elapsed_time(e1))
     clocks = sampler.stop(t_begin, t_end)
     launches = sph.launch_count() - l0
-    pairs_last, nmax, nmin = sph.neighbor_stats()
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    pairs_last = allsum(sph.neighbor_stats()[0])
+    if slab:
+        sph.status()
     ms_per_step = ms / args.steps
-    value = n * world * args.steps / (ms * 1e-3)
+    value = n_total * args.steps / (ms * 1e-3)
 
     # ---- per-kernel durations (CUDA events inside the library, same stream) --
     sph.set_params(enable_timers=1)
@@ -189,51 +274,71 @@ def run_ours(args):
         phase += np.array(sph.timings_ms())
     phase /= reps
     sph.set_params(enable_timers=0)
-    force_ms = float(phase[4])
+    dens_ms, force_ms = float(phase[2]), float(phase[4])
     hbm, peak_kind = measured_peaks()
-    achieved = ALG_BYTES_FORCE * n / (force_ms * 1e-3) / 1e9 if force_ms > 0 else 0.0
+    n_dev = n
+    achieved = ALG_BYTES_DENSITY * n_dev / (dens_ms * 1e-3) / 1e9 if dens_ms > 0 else 0.0
 
-    # ---- end to end through the host-buffer call ----------------------------
-    pos_h.numpy()[...] = 0
-    S.scene_lattice(nx, ny, nz, d, origin, out=pos_h.numpy())
-    vel_h.zero_()
+    # ---- end to end through host buffers -------------------------------------
+    # every step: H2D of positions / velocities / masses (/ ids) from pinned memory,
+    # the step, D2H of the new positions and velocities into pinned memory
+    load_scene()
     e2e_steps = max(1, min(args.steps, 10))
+
+    def e2e_step():
+        if not slab:
+            sph.step_host_ptr(pos_h.data_ptr(), vel_h.data_ptr(), mass_h.data_ptr())
+        else:
+            sph._check(sph._lib.sphb200_upload_slab(sph._h, n, pos_h.data_ptr(), vel_h.data_ptr(),
+                                                    mass_h.data_ptr(), gid_h.data_ptr()))
+            sph.step_n(1)
+            sph._check(sph._lib.sphb200_download(sph._h, S.Field.POSITION, pos_h.data_ptr(), pos_h.numel() * 4))
+            sph._check(sph._lib.sphb200_download(sph._h, S.Field.VELOCITY, vel_h.data_ptr(), vel_h.numel() * 4))
     for _ in range(2):
-        sph.step_host_ptr(pos_h.data_ptr(), vel_h.data_ptr(), mass_h.data_ptr())
+        e2e_step()
+    if slab:
+        load_scene()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        sph.step_host_ptr(pos_h.data_ptr(), vel_h.data_ptr(), mass_h.data_ptr())
+        e2e_step()
+        if slab:
+            gid_h.numpy()[:n] = sc["gids"].view(np.int32)   # slot order is unchanged by the download
     barrier()
-    e2e_s = time.perf_counter() - t0
-    e2e_value = n * world * e2e_steps / e2e_s
+    e2e_s = allmax(time.perf_counter() - t0)
+    e2e_value = n_total * e2e_steps / e2e_s
+    h2d = (32 if slab else 28) * n
+    d2h = 24 * (capacity if slab else n)
 
     out = {
         "metric": "particle-updates/sec", "value": value, "unit": "particle-updates/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "%s: %dx%dx%d jittered lattice = %d particles/GPU, h=0.1, ~%.0f neighbours, "
-                               "voxel grid %s, FULL neighbour mode, gravity+walls on" % (
-                                   name, nx, ny, nz, n, NU, "x".join(map(str, cfg["grid"]))),
-                   "particles": n * world, "neighbor_pairs_per_sec": pairs_last * world / (ms_per_step * 1e-3),
-                   "mean_neighbors": pairs_last / n, "l2": "inputs (>= 512 MB state) larger than the 126 MB L2",
+        "scaling": "strong" if strong and world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": workload, "particles": n_total,
+                   "neighbor_pairs_per_sec": pairs_last / (ms_per_step * 1e-3),
+                   "mean_neighbors": pairs_last / n_total,
+                   "l2": "inputs (>= 512 MB of state per GPU) larger than the 126 MB L2",
                    "step_alg_bytes_per_particle": ALG_BYTES_STEP,
-                   "step_hbm_frac": ALG_BYTES_STEP * n / (ms_per_step * 1e-3) / 1e9 / hbm,
-                   "phase_ms": {"bin_sort_gather": float(phase[0]), "density_eos": float(phase[2]),
-                                "force_integrate": force_ms, "reduce": float(phase[5])}},
+                   "step_hbm_frac": ALG_BYTES_STEP * n_dev / (ms_per_step * 1e-3) / 1e9 / hbm,
+                   "phase_ms_rank0": {"exchange_bin_sort_gather": float(phase[0]), "density_eos": dens_ms,
+                                      "force_integrate": force_ms, "reduce": float(phase[5])}},
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": 28 * n, "d2h_bytes_per_step": 24 * n,
-                "steps": e2e_steps},
+        "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_force_tiled (force+integrate+collide sweep)", "achieved": achieved,
-                     "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None, "peak_kind": peak_kind,
-                     "alg_bytes_per_particle": ALG_BYTES_FORCE, "kernel_ms": force_ms},
+        "roofline": {"bound": "hbm", "kernel": "k_density_tiled (density + EOS + hit-mask stream sweep)",
+                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                     "peak_kind": peak_kind, "alg_bytes_per_particle": ALG_BYTES_DENSITY, "kernel_ms": dens_ms,
+                     "note": "FP32-issue bound, not HBM bound: see DESIGN.md section 5"},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference_sample(steps=10, warmup=1)
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     sph.close()
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ----------------------------------------------------------------------------
@@ -300,10 +405,30 @@ def run_reference(args):
            "config": {"workload": name, "sampled_as": cb["sample"]},
            "cpu_baseline": cb,
            "e2e": {"value": cb["value"], "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+def _claim_stdout():
+    """Libraries (NCCL prints its version banner) must not pollute the one JSON line
+    rank 0 prints: fd 1 is pointed at stderr for the run and the saved descriptor is
+    used for the result."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
+RESULT_OUT = None
+
+
+def emit(obj):
+    RESULT_OUT.write(json.dumps(obj) + "\n")
+    RESULT_OUT.flush()
 
 
 def main():
+    global RESULT_OUT
+    RESULT_OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
@@ -311,6 +436,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--force-slab", action="store_true", help="N=1: run the slab code path as a single slab")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: 16.7M particles per GPU (weak, default) or 16.7M in total (strong)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

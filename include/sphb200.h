@@ -186,6 +186,9 @@ int sphb200_slab_pack(sphb200_ctx* ctx);
 int sphb200_slab_transfer(sphb200_ctx* src, int dir, sphb200_ctx* dst);
 int sphb200_slab_unpack(sphb200_ctx* ctx);
 int sphb200_slab_step_local(sphb200_ctx* ctx);
+/* ghost particles per halo message.  NCCL ranks agree on the largest request at
+ * comm_init; virtual ranks must be given one common value by the caller. */
+int sphb200_slab_set_halo_capacity(sphb200_ctx* ctx, long long ghost_particles);
 /* SPHB200_E_CAPACITY when a halo message or the slot capacity overflowed */
 int sphb200_slab_status(sphb200_ctx* ctx);
 

@@ -95,6 +95,7 @@ API = [
     ("sphb200_slab_transfer", [_VP, C.c_int, _VP], C.c_int),
     ("sphb200_slab_unpack", [_VP], C.c_int),
     ("sphb200_slab_step_local", [_VP], C.c_int),
+    ("sphb200_slab_set_halo_capacity", [_VP, C.c_longlong], C.c_int),
     ("sphb200_slab_status", [_VP], C.c_int),
 ]
 
@@ -414,13 +415,15 @@ class SlabSPH(SPH):
     """One z-slab of a multi-GPU run (one per rank / GPU).  `params.grid_z` is the
     GLOBAL grid and `params.particle_count` the slot capacity of this slab."""
 
-    def __init__(self, params, rank, nranks, z0, z1, nccl_id=None, device=-1):
+    def __init__(self, params, rank, nranks, z0, z1, nccl_id=None, device=-1, halo_capacity=None):
         super().__init__(params, device=device, init_scene=False)
         self.rank, self.nranks, self.z0, self.z1 = rank, nranks, z0, z1
         idbuf = None
         if nccl_id is not None:
             idbuf = (C.c_ubyte * 128).from_buffer_copy(bytes(nccl_id))
         self._check(self._lib.sphb200_comm_init(self._h, rank, nranks, idbuf, z0, z1))
+        if halo_capacity is not None:
+            self._check(self._lib.sphb200_slab_set_halo_capacity(self._h, int(halo_capacity)))
 
     @staticmethod
     def unique_id():

@@ -75,6 +75,7 @@ struct NcclApi
    ncclResult_t (*CommDestroy)(ncclComm_t);
    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
    ncclResult_t (*GroupStart)();
    ncclResult_t (*GroupEnd)();
    const char* (*GetErrorString)(ncclResult_t);
@@ -104,10 +105,11 @@ NcclApi& nccl_api()
       *(void**)&a.CommDestroy = dlsym(h, "ncclCommDestroy");
       *(void**)&a.Send = dlsym(h, "ncclSend");
       *(void**)&a.Recv = dlsym(h, "ncclRecv");
+      *(void**)&a.AllReduce = dlsym(h, "ncclAllReduce");
       *(void**)&a.GroupStart = dlsym(h, "ncclGroupStart");
       *(void**)&a.GroupEnd = dlsym(h, "ncclGroupEnd");
       *(void**)&a.GetErrorString = dlsym(h, "ncclGetErrorString");
-      a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.GroupStart && a.GroupEnd &&
+      a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.Send && a.Recv && a.AllReduce && a.GroupStart && a.GroupEnd &&
              a.GetErrorString;
       if (!a.ok)
          a.why = "libnccl.so.2 lacks a required symbol";
@@ -299,6 +301,32 @@ int require_slab(sphb200_ctx* ctx, const char* what)
 
 }  // namespace
 
+// (re)allocates the four message buffers for `ghost_cap` ghost entries per message.
+// Every rank of a run must use the SAME capacity: a send and its matching receive
+// have to agree on the byte count.
+static int slab_alloc_messages(sphb200_ctx* ctx, long long ghost_cap)
+{
+   SlabComm* c = ctx->comm;
+   if (ghost_cap < 1)
+      ghost_cap = 1;
+   if (ghost_cap > (1ll << 28))
+      return sph_fail(ctx, SPHB200_E_INVALID, "halo capacity too large");
+   c->ghost_cap = (int)ghost_cap;
+   c->mig_cap = (int)(ghost_cap / 4 + 256);
+   c->msg_bytes = sizeof(SlabMsgHeader) + sizeof(SlabEntry) * ((size_t)c->ghost_cap + (size_t)c->mig_cap);
+   for (int d = 0; d < 2; d++)
+   {
+      if (c->send[d]) cudaFree(c->send[d]);
+      if (c->recv[d]) cudaFree(c->recv[d]);
+      c->send[d] = c->recv[d] = nullptr;
+      SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->send[d], c->msg_bytes));
+      SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->recv[d], c->msg_bytes));
+      SPH_CUDA_CHECK(ctx, cudaMemset(c->send[d], 0, sizeof(SlabMsgHeader)));
+      SPH_CUDA_CHECK(ctx, cudaMemset(c->recv[d], 0, sizeof(SlabMsgHeader)));
+   }
+   return SPHB200_OK;
+}
+
 void sph_comm_dev_params(const sphb200_ctx* ctx, DevParams& P)
 {
    const SlabComm* c = ctx->comm;
@@ -443,26 +471,13 @@ int sphb200_comm_init(sphb200_ctx* ctx, int rank, int nranks, const void* id128,
    c->z1 = z1;
    c->zlo = rank > 0 ? z0 - 1 : z0;
    c->zhi = rank < nranks - 1 ? z1 + 1 : z1;
-   // one voxel layer of ghosts; 2.5x the mean layer population as headroom
+   // one voxel layer of ghosts; 2.5x the mean layer population as headroom (agreed
+   // across ranks below: the largest request wins)
    long long per_layer = ((long long)ctx->capacity + (z1 - z0) - 1) / (z1 - z0);
    long long gcap = per_layer * 5 / 2 + 1024;
    if (const char* env = getenv("SPHB200_HALO_CAPACITY"))
       gcap = atoll(env);
-   if (gcap > ctx->capacity)
-      gcap = ctx->capacity;
-   if (gcap < 1)
-      gcap = 1;
-   c->ghost_cap = (int)gcap;
-   c->mig_cap = (int)(gcap / 4 + 256);
-   c->msg_bytes = sizeof(SlabMsgHeader) + sizeof(SlabEntry) * ((size_t)c->ghost_cap + (size_t)c->mig_cap);
    ctx->comm = c;
-   for (int d = 0; d < 2; d++)
-   {
-      SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->send[d], c->msg_bytes));
-      SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->recv[d], c->msg_bytes));
-      SPH_CUDA_CHECK(ctx, cudaMemset(c->send[d], 0, sizeof(SlabMsgHeader)));
-      SPH_CUDA_CHECK(ctx, cudaMemset(c->recv[d], 0, sizeof(SlabMsgHeader)));
-   }
    const size_t cap = (size_t)(ctx->capacity > 0 ? ctx->capacity : 1);
    SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->free_list, sizeof(uint32_t) * cap));
    SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->counters, sizeof(unsigned) * 2));
@@ -490,10 +505,28 @@ int sphb200_comm_init(sphb200_ctx* ctx, int rank, int nranks, const void* id128,
       memcpy(&id, id128, 128);
       SPH_NCCL_CHECK(ctx, N.CommInitRank(&c->nccl, nranks, id, rank));
       c->has_nccl = true;
+      // all ranks must use one message size: take the largest request
+      long long* d_cap = reinterpret_cast<long long*>(c->counters);   // 8 bytes of scratch
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(d_cap, &gcap, sizeof(gcap), cudaMemcpyHostToDevice, ctx->stream));
+      SPH_NCCL_CHECK(ctx, N.AllReduce(d_cap, d_cap, 1, ncclInt64, ncclMax, c->nccl, ctx->stream));
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(&gcap, d_cap, sizeof(gcap), cudaMemcpyDeviceToHost, ctx->stream));
+      SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
    }
    else if (nranks == 1)
       c->has_nccl = true, c->nccl = nullptr;   // single slab: nothing to exchange
-   return SPHB200_OK;
+   return slab_alloc_messages(ctx, gcap);
+}
+
+// virtual ranks (no communicator) cannot negotiate: the caller gives every slab the
+// same halo capacity (ghost particles per message) before the first step
+int sphb200_slab_set_halo_capacity(sphb200_ctx* ctx, long long ghost_particles)
+{
+   int rc = require_slab(ctx, "slab_set_halo_capacity");
+   if (rc)
+      return rc;
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+   return slab_alloc_messages(ctx, ghost_particles);
 }
 
 int sphb200_get_local_count(const sphb200_ctx* ctx, int* owned, int* ghosts)

@@ -78,7 +78,7 @@ def test_virtual_slabs_reproduce_single_gpu_run(nranks):
         # stale.  It is nobody's neighbour, so only its own acceleration row is excluded.
         acc_ref = ref.download(F.ACCELERATION)
         finite = np.isfinite(acc_ref).all(axis=1)
-        assert finite.mean() > 0.999
+        assert finite.mean() > 0.99
         assert np.array_equal(_gather(slabs, F.ACCELERATION)[0][finite], acc_ref[finite])
         assert np.array_equal(_gather(slabs, F.POSITION)[0], ref.download(F.POSITION), equal_nan=True)
         assert np.array_equal(_gather(slabs, F.VELOCITY)[0], ref.download(F.VELOCITY), equal_nan=True)
