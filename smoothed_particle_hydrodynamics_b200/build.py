@@ -62,5 +62,20 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+HEADLESS = os.path.join(HERE, "sph_headless")
+
+
+def build_host(force=False):
+    """The C++ facade (host/sph.cpp, reference `class SPH` interface) + the headless driver."""
+    srcs = [os.path.join(HOST, f) for f in ("sph.cpp", "headless_main.cpp")]
+    deps = srcs + [os.path.join(HOST, f) for f in ("sph.h", "particle.h", "vec3.h")] + [LIB]
+    if force or _newer(HEADLESS, deps):
+        subprocess.check_call(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), "-I", HOST] + srcs +
+                              ["-L", HERE, "-lsphb200", "-Wl,-rpath,$ORIGIN", "-o", HEADLESS])
+    return HEADLESS
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_host(force="--force" in sys.argv))

@@ -1,0 +1,45 @@
+"""The C++ facade (host/sph.cpp: the reference's `class SPH` interface over the
+C ABI) through the headless driver -- the reference's `./sph r` (main.cpp:23-28 ->
+SPH::run, sph.cpp:149-187): step count, the four log files and their formats,
+energies against the reference's own log (golden fixture)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "smoothed_particle_hydrodynamics_b200", "sph_headless")
+
+
+def test_headless_run_writes_the_reference_logs(tmp_path, golden_default):
+    if not os.path.exists(EXE):
+        pytest.fail("sph_headless is not built (python -m smoothed_particle_hydrodynamics_b200.build)")
+    out = tmp_path / "out"
+    r = subprocess.run([EXE, "19", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Directory created" in r.stdout
+    energy = (out / "energy.txt").read_text().splitlines()
+    assert energy[0] == "Step, Kinetic Energy, Potential Energy, Total Energy"
+    rows = np.array([[float(x) for x in line.split(",")] for line in energy[1:]])
+    assert rows.shape == (20, 4)                        # totalSteps + 1 steps, like the reference loop
+    assert np.array_equal(rows[:, 0], np.arange(20))
+    ref = golden_default["energy_20"].astype(np.float64)   # the reference's own energies, 20 steps
+    # first steps tightly (6 printed digits); later steps loosely (chaotic trajectories)
+    np.testing.assert_allclose(rows[:3, 1:3], ref[:3], rtol=2e-5)
+    np.testing.assert_allclose(rows[:, 1:3], ref, rtol=2e-3)
+    np.testing.assert_allclose(rows[:, 3], rows[:, 1] + rows[:, 2], rtol=1e-4)
+    assert energy[1].startswith("0, 4.69595e+06, -8.37892e+06")   # the reference's step-0 line
+    timing = (out / "timing.txt").read_text().splitlines()
+    assert timing[0] == ("Step, Voxelize, Find Neighbors, Compute Density, Compute Pressure, "
+                         "Compute Acceleration, Integrate")
+    assert len(timing) == 21 and all(len(t.split(",")) == 7 for t in timing[1:])
+    am = (out / "angularmomentum.txt").read_text().splitlines()
+    assert am[0] == "Step, Angular Momentum" and am[1] == "0, 0"
+    nb = (out / "neighbors.txt").read_text().splitlines()
+    assert len(nb) == 20
+    avg, mx, mn = [int(x) for x in nb[0].split(",")]
+    cnt = golden_default["nbr_count_1"].astype(np.int64)
+    assert (avg, mx, mn) == (int(cnt.sum()) // cnt.size, int(cnt.max()), min(34, int(cnt.min())))
