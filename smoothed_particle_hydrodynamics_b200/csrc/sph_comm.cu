@@ -663,10 +663,14 @@ int sphb200_slab_transfer(sphb200_ctx* src, int dir, sphb200_ctx* dst)
    if (dir < 0 || dir > 1 || src->comm->msg_bytes != dst->comm->msg_bytes ||
        dst->comm->rank != src->comm->rank + (dir ? 1 : -1))
       return sph_fail(src, SPHB200_E_INVALID, "slab_transfer: contexts are not neighbours in that direction");
+   // the message is complete once src's stream has drained; the copy is ordered on dst's
+   // stream (after dst's last unpack, before its next one).  A plain cudaMemcpy would not
+   // do: device-to-device copies return before they finish and the contexts' non-blocking
+   // streams do not wait for the legacy stream.
    SPH_CUDA_CHECK(src, cudaStreamSynchronize(src->stream));
-   SPH_CUDA_CHECK(dst, cudaStreamSynchronize(dst->stream));   // dst may still be reading its last message
-   SPH_CUDA_CHECK(src, cudaMemcpy(dst->comm->recv[1 - dir], src->comm->send[dir], src->comm->msg_bytes,
-                                  cudaMemcpyDefault));
+   SPH_CUDA_CHECK(dst, cudaMemcpyAsync(dst->comm->recv[1 - dir], src->comm->send[dir], src->comm->msg_bytes,
+                                       cudaMemcpyDefault, dst->stream));
+   SPH_CUDA_CHECK(dst, cudaStreamSynchronize(dst->stream));   // src may repack its send buffer right away
    return SPHB200_OK;
 }
 
