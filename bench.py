@@ -111,7 +111,7 @@ def workload_spec(name):
 
 
 # ----------------------------------------------------------------------------
-def column_scene(world, rank, strong):
+def column_scene(world, rank, strong, sites_xy=(256, 128), planes=512):
     """Multi-GPU scene: ONE continuous jittered lattice column along z, 256x128 sites
     in x,y and 512 z-sites per GPU (weak scaling, SURVEY config 4: 16.7M per GPU) or 512
     z-sites in total (strong scaling, config 3), lifted 16 voxels off the floor and
@@ -119,8 +119,8 @@ def column_scene(world, rank, strong):
     owns the same number of lattice planes (+-1).  Each rank generates only its own
     particles (counter-based jitter) and keeps those whose voxel layer it owns."""
     import smoothed_particle_hydrodynamics_b200 as S
-    nx, ny = 256, 128
-    nz = 512 if strong else 512 * world
+    nx, ny = sites_xy
+    nz = planes if strong else planes * world
     d = scenes.lattice_spacing(0.1, NU)
     vox = 0.2
     oz = 3
