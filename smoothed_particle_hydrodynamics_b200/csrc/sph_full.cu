@@ -8,8 +8,8 @@
 //   force sweep   : spiky pressure + viscosity (computeAcceleration,
 //                   sph.cpp:778-934) + integrate (937-1022) + wall collision
 //                   (1025-1148) + energy / neighbour statistics
-// A CTA owns a 4x4x4 block of fine cells, stages the block plus its one-cell halo
-// (36 x-contiguous row segments of the cell-sorted arrays) in shared memory, and
+// A CTA owns an 8x8x4 block of fine cells, stages the block plus its one-cell halo
+// (60 x-contiguous row segments of the cell-sorted arrays) in shared memory, and
 // each thread walks the 9 x-runs of its particle there.
 //
 // The density sweep has to touch every candidate anyway, so it also records which
@@ -20,19 +20,19 @@
 // second scan -- applying the exact reference test (sph.cpp:633-653) and the pair
 // body in ascending cell order (the order the in-loop viscosity scaling of
 // sph.cpp:880-882 depends on).  No per-particle neighbour list is stored.
-// Blocks too dense for shared memory are split (4x4x2, 4x2x2, 2x2x2) and, past
+// Blocks too dense for shared memory are split (8x8x2, 8x4x2, 4x4x2) and, past
 // that, processed straight from global memory (same arithmetic, scan based).
 #include "sph_math.cuh"
 
 namespace
 {
 
-constexpr int TB = 4;                       // tile edge in fine cells
-constexpr int HROWS = (TB + 2) * (TB + 2);  // halo rows (y,z) of a full tile
-constexpr int CSW = TB + 3;                 // cell_start entries per halo row
-constexpr int TROWS = TB * TB;              // target rows of a full tile
-constexpr int kTileThreads = 256;
-constexpr int kCap = 2400;                  // staged particles per (sub-)tile; BOTH sweeps must lay tiles out
+constexpr int TBX = 8, TBY = 8, TBZ = 4;    // tile extent in fine cells (x rows are contiguous in memory)
+constexpr int HROWS = (TBY + 2) * (TBZ + 2);   // halo rows (y,z) of a full tile
+constexpr int CSW = TBX + 3;                // cell_start entries per halo row
+constexpr int TROWS = TBY * TBZ;            // target rows of a full tile (<= 32: one warp scans them)
+constexpr int kTileThreads = 512;
+constexpr int kCap = 6600;                  // staged particles per (sub-)tile; BOTH sweeps must lay tiles out
                                             // identically (stream offsets), so they share the capacity
 constexpr int WCAP = 32;                    // hit-mask records per particle (32 candidates each)
 constexpr unsigned kNoStream = 0xffu;       // info.nw value: no stream, scan instead
@@ -443,20 +443,20 @@ __device__ __forceinline__ Target locate_target(const SubTile& t, const TileLayo
    return T;
 }
 
-// picks the sub-division level of this CTA's tile: 0 = 4x4x4 ... 3 = 2x2x2,
+// picks the sub-division level of this CTA's tile: 0 = whole tile ... 3 = every axis halved,
 // 4 = nothing fits (process from global memory).  Evaluated by warp 0.
 __device__ int choose_level(const DevParams& P, int X0, int Y0, int Z0, const uint32_t* __restrict__ cell_start,
                             int cap)
 {
    for (int level = 0; level < 4; level++)
    {
-      int bz = level >= 1 ? TB / 2 : TB;
-      int by = level >= 2 ? TB / 2 : TB;
-      int bx = level >= 3 ? TB / 2 : TB;
+      int bz = level >= 1 ? TBZ / 2 : TBZ;
+      int by = level >= 2 ? TBY / 2 : TBY;
+      int bx = level >= 3 ? TBX / 2 : TBX;
       bool fits = true;
-      for (int z = 0; z < TB && fits; z += bz)
-         for (int y = 0; y < TB && fits; y += by)
-            for (int x = 0; x < TB && fits; x += bx)
+      for (int z = 0; z < TBZ && fits; z += bz)
+         for (int y = 0; y < TBY && fits; y += by)
+            for (int x = 0; x < TBX && fits; x += bx)
             {
                SubTile t = {X0 + x, Y0 + y, Z0 + z, bx, by, bz};
                fits = halo_population(P, t, cell_start) <= cap;
@@ -469,11 +469,11 @@ __device__ int choose_level(const DevParams& P, int X0, int Y0, int Z0, const ui
 
 __device__ __forceinline__ void tile_origin(const DevParams& P, int& X0, int& Y0, int& Z0)
 {
-   int tx = (P.fx + TB - 1) / TB, ty = (P.fy + TB - 1) / TB;
+   int tx = (P.fx + TBX - 1) / TBX, ty = (P.fy + TBY - 1) / TBY;
    int b = blockIdx.x;
-   X0 = (b % tx) * TB;
-   Y0 = ((b / tx) % ty) * TB;
-   Z0 = (b / (tx * ty)) * TB;
+   X0 = (b % tx) * TBX;
+   Y0 = ((b / tx) % ty) * TBY;
+   Z0 = (b / (tx * ty)) * TBZ;
 }
 
 // particles of the un-haloed tile (quick exit for empty space); warp 0
@@ -483,11 +483,11 @@ __device__ int tile_population(const DevParams& P, int X0, int Y0, int Z0, const
    int sum = 0;
    if (lane < TROWS)
    {
-      int y = Y0 + lane % TB, z = Z0 + lane / TB;
+      int y = Y0 + lane % TBY, z = Z0 + lane / TBY;
       if (y < P.fy && z < P.fz)
       {
          int row = (z * P.fy + y) * P.fx;
-         sum = (int)cell_start[row + min(X0 + TB, P.fx)] - (int)cell_start[row + X0];
+         sum = (int)cell_start[row + min(X0 + TBX, P.fx)] - (int)cell_start[row + X0];
       }
    }
    return warp_sum(sum);
@@ -566,7 +566,7 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
    }
 }
 
-__global__ void __launch_bounds__(kTileThreads, 4)
+__global__ void __launch_bounds__(kTileThreads, 2)
    k_density_tiled(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ cell_start,
                    const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ vel4,
                    float4* __restrict__ s_posA4, float4* __restrict__ s_velB4, float* __restrict__ s_rho,
@@ -592,12 +592,12 @@ __global__ void __launch_bounds__(kTileThreads, 4)
    if (s_pop == 0)
       return;
    const int level = s_level;
-   const int bz = (level >= 1 && level < 4) ? TB / 2 : TB;
-   const int by = (level >= 2 && level < 4) ? TB / 2 : TB;
-   const int bx = (level >= 3 && level < 4) ? TB / 2 : TB;
-   for (int z = 0; z < TB; z += bz)
-      for (int y = 0; y < TB; y += by)
-         for (int x = 0; x < TB; x += bx)
+   const int bz = (level >= 1 && level < 4) ? TBZ / 2 : TBZ;
+   const int by = (level >= 2 && level < 4) ? TBY / 2 : TBY;
+   const int bx = (level >= 3 && level < 4) ? TBX / 2 : TBX;
+   for (int z = 0; z < TBZ; z += bz)
+      for (int y = 0; y < TBY; y += by)
+         for (int x = 0; x < TBX; x += bx)
          {
             SubTile t = {X0 + x, Y0 + y, Z0 + z, bx, by, bz};
             setup_layout(P, t, cell_start, level < 4, L);
@@ -809,7 +809,7 @@ int sph_full_configure(sphb200_ctx* ctx)
 int sph_full_tile_count(const sphb200_ctx* ctx)
 {
    int fx = 2 * ctx->params.grid_x, fy = 2 * ctx->params.grid_y, fz = 2 * ctx->params.grid_z;
-   return ((fx + TB - 1) / TB) * ((fy + TB - 1) / TB) * ((fz + TB - 1) / TB);
+   return ((fx + TBX - 1) / TBX) * ((fy + TBY - 1) / TBY) * ((fz + TBZ - 1) / TBZ);
 }
 
 int sph_step_full(sphb200_ctx* ctx)
@@ -832,7 +832,7 @@ int sph_step_full(sphb200_ctx* ctx)
    const bool tiled = ctx->params.kernel_variant != 1;
    if (tiled)
    {
-      int tiles = ((P.fx + TB - 1) / TB) * ((P.fy + TB - 1) / TB) * ((P.fz + TB - 1) / TB);   // local grid
+      int tiles = ((P.fx + TBX - 1) / TBX) * ((P.fy + TBY - 1) / TBY) * ((P.fz + TBZ - 1) / TBZ);   // local grid
       k_density_tiled<<<tiles, kTileThreads, density_smem(), st>>>(P, ctx->s_pos4, ctx->cell_start, ctx->idx_order,
                                                                   ctx->vel4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
                                                                   ctx->hit_rec, ctx->hit_info);

@@ -341,3 +341,54 @@ def test_step_host_roundtrip_matches_device_resident_path(golden_default):
     check_state(vel, g["vel_1"], 1.0)
     assert sph.launch_count() > 0
     sph.close()
+
+
+# ------------------------------------------------ full-size, size-independent properties
+@pytest.mark.parametrize("name", ["dambreak_1m", "dambreak_16m"])
+def test_full_size_properties(name):
+    """At BASELINE.json's sizes the oracle is too slow; check what must hold at any
+    size: the neighbour relation is symmetric (sum of counts even, counts == list
+    degrees on a sample), tiled and flat kernels agree exactly on integers and to
+    rounding on fields, density >= 0, momentum change == gravity impulse for the
+    bulk, particle count conserved (no NaN, nothing leaves the box with walls on)."""
+    cfg = scenes.CONFIGS[name]
+    nx, ny, nz = cfg["sites"]
+    n = nx * ny * nz
+    d = scenes.lattice_spacing(0.1, 40)
+    pos = S.scene_lattice(nx, ny, nz, d)
+    vel = np.zeros((n, 3), np.float32)
+    res = []
+    for variant in (0, 1):
+        sph = S.SPH(_full_params(cfg, n, 96, variant), init_scene=False)
+        sph.upload(pos, vel)
+        sph.step_n(1)
+        cnt = sph.download(F.NEIGHBOR_COUNT)
+        rho = sph.download(F.DENSITY)
+        total, mx, mn = sph.neighbor_stats()
+        assert total == int(cnt.astype(np.int64).sum()) and mx == cnt.max() and mn == cnt.min()
+        assert total % 2 == 0                       # i in N(j) <=> j in N(i)
+        assert rho.min() >= 0.0 and np.isfinite(rho).all()
+        if variant == 0 and n <= (1 << 21):
+            sph.build_neighbor_lists()
+            idx = sph.download(F.NEIGHBOR_INDEX)
+            sample = np.random.default_rng(0).choice(n, 2000, replace=False)
+            for i in sample:
+                for j in idx[i, :cnt[i]]:
+                    assert i in idx[j, :cnt[j]]     # symmetry, pair by pair
+        sph.step_n(4)
+        p = sph.download(F.POSITION)
+        v = sph.download(F.VELOCITY)
+        dmax = sph.derived
+        assert np.isfinite(p).all() and np.isfinite(v).all()
+        assert (p >= 0).all() and (p[:, 0] <= dmax.max_x).all() and (p[:, 1] <= dmax.max_y).all()
+        res.append((cnt, rho, p, v, sph.energies()))
+        sph.close()
+    assert np.array_equal(res[0][0], res[1][0])
+    np.testing.assert_allclose(res[0][1], res[1][1], rtol=2e-6, atol=1e-3)
+    np.testing.assert_allclose(res[0][2], res[1][2], rtol=1e-5, atol=1e-6)
+    # 33.1 neighbours on average for this lattice (32 on the perfect lattice + jitter)
+    assert 32.0 < res[0][0].mean() < 34.5
+    # the block is at rest: after 5 steps v_y of an interior particle == 5 steps of the
+    # gravity kicks (first half kick with a=g, the rest full) up to the tiny SPH forces
+    vy = res[0][3][:, 1]
+    assert abs(np.median(vy) + 9.8 * 0.001 * 5) < 2e-3
