@@ -89,6 +89,22 @@ __global__ void __launch_bounds__(kThreads) k_fix_cell_order(int cells, const ui
    if (c >= cells)
       return;
    int s = (int)cell_start[c], e = (int)cell_start[c + 1];
+   if (s == e)
+      return;
+   // most cells are already in order (only arrivals of the exchange sit in arbitrary
+   // slots): one linear pass decides, and copies
+   bool sorted = true;
+   uint32_t prev = 0;
+   for (int a = s; a < e; a++)
+   {
+      uint32_t ia = idx_sorted[a];
+      uint32_t ga = gid[ia];
+      sorted = sorted && (a == s || ga > prev);
+      prev = ga;
+      idx_fixed[a] = ia;
+   }
+   if (sorted)
+      return;
    for (int a = s; a < e; a++)
    {
       uint32_t ia = idx_sorted[a];
