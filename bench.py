@@ -39,6 +39,9 @@ from oracle import scenes  # noqa: E402  (input synthesis only)
 ALG_BYTES_STEP = 240.0     # algorithmic bytes per particle-step (whole pipeline)
 ALG_BYTES_FORCE = 72.0     # force+integrate+collide sweep: R(16+16+4) + W(16+16) + R4
 ALG_BYTES_DENSITY = 20.0   # density+EOS sweep: R16 + W4
+# dram__bytes_read.sum + dram__bytes_write.sum of k_density_tiled per launch at 16.7M particles,
+# from the committed `ncu --set full` capture (profiles/r01_ncu_top_kernels_16m.csv)
+NCU_TRAFFIC_DENSITY_16M = 0.848093e9 + 1.528132e9
 NU = 40.0
 
 
@@ -107,6 +110,9 @@ def workload_spec(name):
     nx, ny, nz = cfg["sites"]
     d = scenes.lattice_spacing(0.1, NU)
     origin = [v * 0.2 for v in cfg["origin_vox"]]
+    # sparser lattices (nu < 40) are taller than the configured box: grow it (SURVEY config 5)
+    need = [int(np.ceil(o / 0.2 + s * float(d) / 0.2)) + 2 for o, s in zip(origin, (nx, ny, nz))]
+    cfg = dict(cfg, grid=tuple(max(g, m) for g, m in zip(cfg["grid"], need)))
     return cfg, nx, ny, nz, d, origin
 
 
@@ -328,9 +334,12 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_density_tiled (density + EOS + hit-mask stream sweep)",
-                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                     "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
+                     "traffic": NCU_TRAFFIC_DENSITY_16M if (n_dev == 16777216 and NU == 40.0) else None,
+                     "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_ncu_top_kernels_16m.csv)",
                      "peak_kind": peak_kind, "alg_bytes_per_particle": ALG_BYTES_DENSITY, "kernel_ms": dens_ms,
-                     "note": "FP32-issue bound, not HBM bound: see DESIGN.md section 5"},
+                     "note": "instruction-issue bound (ncu: 82% issue slots busy, DRAM 9% busy), not HBM bound: "
+                             "DESIGN.md section 5"},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference_sample(steps=10, warmup=1)
@@ -353,7 +362,7 @@ def cpu_reference_sample(steps, warmup, sample="dambreak_1m"):
     sp = scenes.scene_params(nu=NU)
     pos = scenes.lattice_scene(nx, ny, nz, d, origin)
     vel = np.zeros((n, 3), np.float32)
-    E = 96
+    E = 96 if NU <= 40.0 else int(NU * 1.6) + 32
     t_steps = []
     pairs = 0
     if kind == "reference":
@@ -436,10 +445,14 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--nu", type=float, default=40.0,
+                    help="lattice spacing for this many neighbours in the continuum limit (config 5 sweep: 30/60/120)")
     ap.add_argument("--force-slab", action="store_true", help="N=1: run the slab code path as a single slab")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: 16.7M particles per GPU (weak, default) or 16.7M in total (strong)")
     args = ap.parse_args()
+    global NU
+    NU = float(args.nu)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)
