@@ -392,3 +392,95 @@ def test_full_size_properties(name):
     # gravity kicks (first half kick with a=g, the rest full) up to the tiny SPH forces
     vy = res[0][3][:, 1]
     assert abs(np.median(vy) + 9.8 * 0.001 * 5) < 2e-3
+
+
+# ------------------------------------------------------ more of the parameter space
+def test_full_dense_lattice_120_neighbours_vs_oracle():
+    """~115 neighbours per particle: several 32-candidate chunks per run, more hit-mask
+    records than the force sweep keeps in shared memory, sub-divided tiles."""
+    cfg = scenes.CONFIGS["dambreak_16k"]
+    nx, ny, nz = cfg["sites"]
+    n = nx * ny * nz
+    d = scenes.lattice_spacing(0.1, 120)
+    pos = scenes.lattice_scene(nx, ny, nz, d)
+    vel = np.random.default_rng(2).normal(0, 0.5, (n, 3)).astype(np.float32)
+    p = _full_params(cfg, n, 256)
+    p.rho0 = float(np.float32(1.0) / (d * d * d))
+    sph = S.SPH(p, init_scene=False)
+    o = _full_oracle(cfg, n, 256, p)
+    sph.upload(pos, vel)
+    o.set_state(pos, vel)
+    o.step(O_FULL, True, True)
+    sph.step_n(1)
+    assert o.count.max() > 100
+    _compare_full_step(sph, o, "nu=120", conditioned=True)
+    sph.close()
+
+
+@pytest.mark.parametrize("mode", ["sampled", "full"])
+def test_simulation_scale_and_runtime_setters_vs_oracle(mode):
+    """mSimulationScale != 1 (sph.cpp:48: scaled distances, kernels, position step) and
+    the runtime setters (sph.cpp:1225-1289) applied between steps."""
+    rng = np.random.default_rng(9)
+    if mode == "sampled":
+        n, grid, E = 32768, (32, 32, 32), 32
+        pos = (rng.random((n, 3)) * 1.6 + 2.4).astype(np.float32)
+        base = S.default_params(simulation_scale=0.5)
+        o = OracleSPH(init_scene=False, simulation_scale=0.5)
+    else:
+        cfg = scenes.CONFIGS["dambreak_16k"]
+        nx, ny, nz = cfg["sites"]
+        n, grid, E = nx * ny * nz, cfg["grid"], 96
+        pos = scenes.lattice_scene(nx, ny, nz, scenes.lattice_spacing(0.1, 40))
+        base = _full_params(cfg, n, E, simulation_scale=0.5)
+        # scaled kernels: rest density of the lattice in scaled units is 1/(d*scale)^3
+        base.rho0 = base.rho0 * 8.0
+        o = _full_oracle(cfg, n, E, base)
+        o.set_params(simulation_scale=0.5)
+    vel = rng.normal(0, 2, (n, 3)).astype(np.float32)
+    sph = S.SPH(base, init_scene=False)
+    sph.upload(pos, vel)
+    o.set_state(pos, vel)
+    full = mode == "full"
+    d = sph.derived
+    assert np.float32(d.h_scaled) == np.float32(o.p.hs) and np.float32(d.kernel1) == np.float32(o.p.kernel1)
+    for s in range(3):
+        if s == 1:      # the GUI's "apply" button (sphconfig.cpp:76-95)
+            sph.setStiffness(0.004)
+            sph.setViscosityScalar(0.02)
+            sph.setTimeStep(0.0005)
+            sph.setCflLimit(500.0)
+            sph.setDamping(0.01)
+            o.set_params(stiffness=0.004, viscosity=0.02, time_step=0.0005, cfl_limit=500.0, damping=0.01)
+        o.step(O_FULL if full else O_SAMPLED, full, full)
+        sph.step_n(1)
+        cnt = sph.download(F.NEIGHBOR_COUNT)
+        assert np.array_equal(cnt, o.count)
+        mask = well_conditioned(o, w0_of(d, o.mass)) if full else None
+        check_density(sph.download(F.DENSITY), o.rho, w0_of(d, o.mass), mode)
+        check_acc(sph.download(F.ACCELERATION), o.acc, mode, mask)
+        check_state(sph.download(F.POSITION), o.pos, 1.0, mode, mask)
+        check_state(sph.download(F.VELOCITY), o.vel, 1.0, mode, mask)
+        sph.upload(o.pos, o.vel, o.mass)
+    sph.close()
+
+
+def test_sampled_examine_count_64_vs_oracle():
+    """E = 64 (the reference's `mExamineCount`, sph.cpp:98): the early exit moves to > 56."""
+    rng = np.random.default_rng(4)
+    n = 32768
+    pos = (rng.random((n, 3)) * 1.2 + 2.6).astype(np.float32)      # ~150 particles per voxel
+    vel = rng.normal(0, 5, (n, 3)).astype(np.float32)
+    sph = S.SPH(S.default_params(examine_count=64), init_scene=False)
+    o = OracleSPH(examine=64, init_scene=False)
+    sph.upload(pos, vel)
+    o.set_state(pos, vel)
+    o.step(O_SAMPLED)
+    sph.step_n(1)
+    cnt = sph.download(F.NEIGHBOR_COUNT)
+    assert np.array_equal(cnt, o.count) and cnt.max() > 32
+    nb, nd = sparse_lists(sph.download(F.NEIGHBOR_INDEX), sph.download(F.NEIGHBOR_DISTANCE), cnt)
+    onb, ond = sparse_lists(o.nbr, o.dist, o.count)
+    assert np.array_equal(nb, onb) and np.array_equal(nd, ond)
+    check_state(sph.download(F.POSITION), o.pos, 1.0)
+    sph.close()
