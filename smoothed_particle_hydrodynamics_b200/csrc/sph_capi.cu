@@ -405,6 +405,12 @@ int sphb200_upload_state(sphb200_ctx* ctx, const float* pos_xyz, const float* ve
       ctx->launches++;
       SPH_CUDA_CHECK(ctx, cudaGetLastError());
    }
+   // all masses equal (the reference never sets anything but 1, sph.cpp:88): lets the
+   // density sweep factor the mass out of its inner loop
+   ctx->uniform_mass = true;
+   if (mass)
+      for (int i = 1; i < n && ctx->uniform_mass; i++)
+         ctx->uniform_mass = mass[i] == mass[0];
    ctx->n_local = ctx->n_owned = n;
    ctx->lists_valid = false;
    ctx->snapshot_valid = false;

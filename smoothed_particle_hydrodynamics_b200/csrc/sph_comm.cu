@@ -585,6 +585,12 @@ int sphb200_upload_slab(sphb200_ctx* ctx, int count, const float* pos_xyz, const
       ctx->launches++;
       SPH_CUDA_CHECK(ctx, cudaGetLastError());
    }
+   // migrants bring their own masses: the uniform-mass fast path is only safe when
+   // every rank uploads unit masses (the reference's only value, sph.cpp:88)
+   ctx->uniform_mass = true;
+   if (mass)
+      for (int i = 0; i < count && ctx->uniform_mass; i++)
+         ctx->uniform_mass = mass[i] == 1.0f;
    ctx->n_owned = count;
    ctx->lists_valid = false;
    ctx->snapshot_valid = false;

@@ -196,17 +196,11 @@ __device__ __forceinline__ ForceI make_force_i(const DevParams& P, float4 pi, fl
 }
 
 // density sweep epilogue for sorted particle k
-__device__ __forceinline__ void density_store(const DevParams& P, int k, float4 pi, float sum,
+__device__ __forceinline__ void density_store(const DevParams& P, int k, float4 pi, float rho,
                                               const uint32_t* __restrict__ idx_sorted,
                                               const float4* __restrict__ vel4, float4* __restrict__ s_posA4,
                                               float4* __restrict__ s_velB4, float* __restrict__ s_rho)
 {
-   // the particle itself sat in the centre run at d2 = 0: remove its own term
-   // (the reference skips realIndex == particleIndex, sph.cpp:737).  Evaluated
-   // through the same expression so that a NaN position (term 0) stays consistent
-   // and an isolated particle gets exactly 0.
-   float self = density_term(0.0f, pi.x, pi.y, pi.z, pi, P.hs2, P.scale * P.scale);
-   float rho = P.k1 * (sum - self);
    float fA, fB;
    sph_force_coeffs(P, rho, pi.w, fA, fB);
    float4 v = __ldg(&vel4[idx_sorted[k]]);
@@ -288,7 +282,8 @@ __global__ void __launch_bounds__(kFlatThreads)
    for (int r = 0; r < 9; r++)
       for (int j = b[r]; j < e[r]; j++)
          sum = density_term(sum, pi.x, pi.y, pi.z, __ldg(&s_pos4[j]), P.hs2, scale2);
-   density_store(P, k, pi, sum, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
+   float self = density_term(0.0f, pi.x, pi.y, pi.z, pi, P.hs2, scale2);   // own term (0 for a NaN position)
+   density_store(P, k, pi, P.k1 * (sum - self), idx_sorted, vel4, s_posA4, s_velB4, s_rho);
 }
 
 // ---- tiled kernels -----------------------------------------------------------
@@ -503,7 +498,17 @@ __device__ __forceinline__ size_t stream_base(int k)
 // Density sweep over one (sub-)tile.  STAGED: candidates come from shared memory
 // and the hit-mask stream is written; otherwise candidates come from global
 // memory and the particle is flagged "scan me" for the force sweep.
-template <bool STAGED>
+//
+// The inner loop is bound by the FMA pipe (ncu r1-final: 24.7 cycles per candidate
+// and scheduler for 12 FMA-class instructions -- 3-operand FP32 ops issue every other
+// cycle), so the fast path is written for the fewest FMA-class operations:
+//   UNIT (simulation scale == 1): t = hs2 - dx^2 - dy^2 - dz^2 as three chained FMAs
+//   instead of mul + 2 fma (d2) + fma (t) + fma (hit test); the hit bit comes from a
+//   compare (ALU pipe) against -1e-5 hs2;
+//   UMASS (all masses equal, as in the reference, sph.cpp:88,105-108): the mass is
+//   factored out of the sum (one multiply less per candidate).
+// 8 FMA-class instructions per candidate instead of 12.
+template <bool STAGED, bool UNIT, bool UMASS>
 __device__ __forceinline__ void density_targets(const DevParams& P, const SubTile& t, const TileLayout& L,
                                                 const float4* __restrict__ src,
                                                 const uint32_t* __restrict__ idx_sorted,
@@ -512,7 +517,7 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
                                                 uint2* __restrict__ hit_rec, unsigned* __restrict__ hit_info)
 {
    const float scale2 = P.scale * P.scale;
-   const float neg_lim = -1.00001f * P.hs2;   // enlarged radius: a superset of the exact d2 < h2 test
+   const float tmin = -1e-5f * P.hs2;         // enlarged radius: a superset of the exact d2 < h2 test
    for (int tnum = threadIdx.x; tnum < L.ntargets; tnum += blockDim.x)
    {
       Target T = locate_target(t, L, tnum);
@@ -533,20 +538,25 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
             const float4* p = src + c0;
             const int n = min(32, e - c0);
             const float4* pe = p + n;
-            // hit bit of a candidate = sign bit of (d2*scale^2 - hs2 + tmin) < 0, shifted
-            // into the mask MSB-first: after the chunk candidate i sits at bit 31 - i
+            // one hit bit per candidate (the sign of tmin - t), shifted in at the LSB: after
+            // the chunk candidate i sits at bit 31 - i
             unsigned mask = 0;
 #pragma unroll 4
             for (; p < pe; p++)
             {
                float4 pj = STAGED ? *p : __ldg(p);
                float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-               float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-               float tt = fmaf(-d2, scale2, P.hs2);
-               float u = fmaf(d2, scale2, neg_lim);
-               mask = __funnelshift_l(__float_as_uint(u), mask, 1);
+               float tt;
+               if (UNIT)
+                  tt = fmaf(-dz, dz, fmaf(-dy, dy, fmaf(-dx, dx, P.hs2)));
+               else
+                  tt = fmaf(-fmaf(dz, dz, fmaf(dy, dy, dx * dx)), scale2, P.hs2);
+               mask = __funnelshift_l(__float_as_uint(tmin - tt), mask, 1);   // sign bit: tt > tmin
                float tc = fmaxf(tt, 0.0f);
-               sum = fmaf(pj.w * tc, tc * tc, sum);
+               if (UMASS)
+                  sum = fmaf(tc * tc, tc, sum);
+               else
+                  sum = fmaf(pj.w * tc, tc * tc, sum);
             }
             mask <<= (32 - n);
             if (STAGED && mask != 0u)
@@ -562,10 +572,16 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
          hit_info[T.k] = nw <= WCAP ? ((unsigned)nw | ((unsigned)nhits << 8)) : kNoStream;
       else
          hit_info[T.k] = kNoStream;
-      density_store(P, T.k, pi, sum, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
+      // the particle itself sat in the centre run with t = hs2: remove its own term (the
+      // reference skips realIndex == particleIndex, sph.cpp:737); a NaN position has term 0
+      float t_self = (pi.x == pi.x && pi.y == pi.y && pi.z == pi.z) ? P.hs2 : 0.0f;
+      float self = UMASS ? (t_self * t_self) * t_self : __fmul_rn(pi.w * t_self, t_self * t_self);
+      float rho = UMASS ? (P.k1 * pi.w) * (sum - self) : P.k1 * (sum - self);
+      density_store(P, T.k, pi, rho, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
    }
 }
 
+template <bool UNIT, bool UMASS>
 __global__ void __launch_bounds__(kTileThreads, 2)
    k_density_tiled(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ cell_start,
                    const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ vel4,
@@ -607,11 +623,12 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                {
                   stage_rows(t, L, s_pos4, sp);
                   __syncthreads();
-                  density_targets<true>(P, t, L, sp, idx_sorted, vel4, s_posA4, s_velB4, s_rho, hit_rec, hit_info);
+                  density_targets<true, UNIT, UMASS>(P, t, L, sp, idx_sorted, vel4, s_posA4, s_velB4, s_rho, hit_rec,
+                                                     hit_info);
                }
                else
-                  density_targets<false>(P, t, L, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho, hit_rec,
-                                         hit_info);
+                  density_targets<false, UNIT, UMASS>(P, t, L, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho,
+                                                      hit_rec, hit_info);
             }
             __syncthreads();   // smem and layout are reused by the next sub-tile
          }
@@ -797,8 +814,12 @@ size_t density_smem() { return sizeof(float4) * (size_t)kCap; }
 
 int sph_full_configure(sphb200_ctx* ctx)
 {
-   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)density_smem()));
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_tiled<true, true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem()));
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_tiled<true, false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem()));
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_tiled<false, false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem()));
    // hit-mask stream: WCAP records per particle, interleaved per 32 sorted particles
    size_t groups = ((size_t)ctx->capacity + 31) / 32;
    SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->hit_rec, sizeof(uint2) * (groups ? groups : 1) * WCAP * 32));
@@ -833,9 +854,12 @@ int sph_step_full(sphb200_ctx* ctx)
    if (tiled)
    {
       int tiles = ((P.fx + TBX - 1) / TBX) * ((P.fy + TBY - 1) / TBY) * ((P.fz + TBZ - 1) / TBZ);   // local grid
-      k_density_tiled<<<tiles, kTileThreads, density_smem(), st>>>(P, ctx->s_pos4, ctx->cell_start, ctx->idx_order,
-                                                                  ctx->vel4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
-                                                                  ctx->hit_rec, ctx->hit_info);
+      auto kd = k_density_tiled<false, false>;
+      if (P.scale == 1.0f)
+         kd = ctx->uniform_mass ? k_density_tiled<true, true> : k_density_tiled<true, false>;
+      kd<<<tiles, kTileThreads, density_smem(), st>>>(P, ctx->s_pos4, ctx->cell_start, ctx->idx_order, ctx->vel4,
+                                                     ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->hit_rec,
+                                                     ctx->hit_info);
    }
    else
       k_density_flat<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, st>>>(

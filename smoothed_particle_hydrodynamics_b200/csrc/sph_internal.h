@@ -105,6 +105,7 @@ struct sphb200_ctx
    float* rho;            // N  (original order)
    float4* acc4;          // N  (original order)
    int* voxel_id;         // N  (original order)
+   bool uniform_mass;     // every particle has the same mass (checked at upload): density fast path
    bool lists_valid;
    bool voxel_ids_valid;  // voxel_id[] matches the last binning / current upload
    bool snapshot_valid;   // sorted snapshot + cell table of the last FULL step present

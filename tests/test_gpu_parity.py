@@ -309,8 +309,10 @@ def test_full_tiled_equals_flat_bitwise_on_integers_and_close_on_fields():
                     sph.energies()))
         sph.close()
     assert np.array_equal(out[0][0], out[1][0])
-    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-5)
-    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-5, atol=1e-6)
+    # three steps of two different (equally valid) FP32 evaluation orders: rounding-level
+    # differences of the state feed back into the density
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-4)
+    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(out[0][3], out[1][3], rtol=1e-5)
 
 
