@@ -32,8 +32,8 @@ constexpr int HROWS = (TBY + 2) * (TBZ + 2);   // halo rows (y,z) of a full tile
 constexpr int CSW = TBX + 3;                // cell_start entries per halo row
 constexpr int TROWS = TBY * TBZ;            // target rows of a full tile (<= 32: one warp scans them)
 constexpr int kTileThreads = 512;
-constexpr int kCap = 6600;                  // staged particles per (sub-)tile; BOTH sweeps must lay tiles out
-                                            // identically (stream offsets), so they share the capacity
+constexpr int kCap = 6600;                  // staged particles per (sub-)tile, equal masses (12 B each)
+constexpr int kCapMass = 4948;              // ... with per-particle masses (16 B each): same 79 KB, 2 CTAs per SM
 constexpr int WCAP = 32;                    // hit-mask records per particle (32 candidates each)
 constexpr unsigned kNoStream = 0xffu;       // info.nw value: no stream, scan instead
 constexpr int RSM = 16;                     // records per thread kept in shared memory by the force sweep
@@ -49,6 +49,8 @@ struct TileLayout
    int tgt_off[TROWS + 1];   // prefix of target counts per target row
    int total;                // staged particles
    int ntargets;
+   int rowk[TROWS];          // sorted index of target t of row r = rowk[r] + t
+   unsigned short tcell[kCap];   // per target: lx | r << 4 | hr0 << 9  (its cell; see locate_target)
 };
 
 // ---- pair arithmetic ---------------------------------------------------------
@@ -79,6 +81,45 @@ __device__ __forceinline__ float sph_rcp_approx(float x)
    float r;
    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
    return r;
+}
+
+// ---- packed FP32 (sm_100a FFMA2 / FADD2): two candidates per instruction -------
+// A 64-bit register pair holds the same coordinate of two consecutive candidates.
+// tools/ubench_f32x2.cu: the packed density loop costs 8.9 cycles per candidate and
+// scheduler against 14.0 for the scalar one (B200), same arithmetic.
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c)
+{
+   f32x2 r;
+   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+   return r;
+}
+
+__device__ __forceinline__ f32x2 fadd2(f32x2 a, f32x2 b)
+{
+   f32x2 r;
+   asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+   return r;
+}
+
+__device__ __forceinline__ f32x2 fmul2(f32x2 a, f32x2 b)
+{
+   f32x2 r;
+   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+   return r;
+}
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi)
+{
+   f32x2 r;
+   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+   return r;
+}
+
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi)
+{
+   asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
 }
 
 struct ForceI     // per-target constants of computeAcceleration (sph.cpp:785-798)
@@ -354,7 +395,11 @@ __device__ void setup_layout(const DevParams& P, const SubTile& t, const uint32_
             g0 = L.cs[hr][0];
             len = L.cs[hr][csw - 1] - g0;
          }
-         int incl = len;
+         // staged rows start on a group boundary (4 candidates): the packed sweep widens
+         // its runs to whole groups and must stay inside the row (stage_rows_packed
+         // fills the slack with far-away sentinels)
+         const int plen = (len + 3) & ~3;
+         int incl = plen;
 #pragma unroll
          for (int o = 1; o < 32; o <<= 1)
          {
@@ -366,7 +411,7 @@ __device__ void setup_layout(const DevParams& P, const SubTile& t, const uint32_
          {
             L.row_g0[hr] = g0;
             L.row_len[hr] = len;
-            L.row_delta[hr] = staged ? (carry + incl - len) - g0 : 0;
+            L.row_delta[hr] = staged ? (carry + incl - plen) - g0 : 0;
          }
          carry += __shfl_sync(0xffffffffu, incl, 31);
       }
@@ -397,6 +442,23 @@ __device__ void setup_layout(const DevParams& P, const SubTile& t, const uint32_
       }
    }
    __syncthreads();
+   // target -> cell table (staged tiles hold at most kCap particles): one thread per
+   // target cell writes the code of its particles
+   const int trows = t.by * t.bz;
+   for (int c = threadIdx.x; staged && c < trows * t.bx; c += blockDim.x)
+   {
+      int r = c / t.bx, x = c - r * t.bx + 1;
+      int hr0 = (r / t.by + 1) * (t.by + 2) + (r % t.by + 1);
+      int first = L.cs[hr0][1];
+      int t0 = L.tgt_off[r] + (L.cs[hr0][x] - first);
+      int cnt = L.cs[hr0][x + 1] - L.cs[hr0][x];
+      unsigned short code = (unsigned short)(x | (r << 4) | (hr0 << 9));
+      for (int i = 0; i < cnt; i++)
+         L.tcell[t0 + i] = code;
+      if (x == 1)
+         L.rowk[r] = first - L.tgt_off[r];
+   }
+   __syncthreads();
 }
 
 // copies the halo rows of `src` (global, cell-sorted) into shared memory
@@ -420,8 +482,9 @@ struct Target
    int lx;       // cell column inside the halo row table (1..bx)
 };
 
-// maps flat target number -> particle and its cell (all from the smem tables)
-__device__ __forceinline__ Target locate_target(const SubTile& t, const TileLayout& L, int tnum)
+// maps flat target number -> particle and its cell by searching the prefix tables
+// (unstaged fallback: any number of targets)
+__device__ __forceinline__ Target locate_target_search(const SubTile& t, const TileLayout& L, int tnum)
 {
    int trows = t.by * t.bz;
    int r = 0;
@@ -435,6 +498,17 @@ __device__ __forceinline__ Target locate_target(const SubTile& t, const TileLayo
    for (int i = 2; i <= t.bx; i++)
       lx += (T.k >= L.cs[T.hr0][i]) ? 1 : 0;
    T.lx = lx;
+   return T;
+}
+
+// maps flat target number -> particle and its cell (table built by setup_layout)
+__device__ __forceinline__ Target locate_target(const TileLayout& L, int tnum)
+{
+   unsigned code = L.tcell[tnum];
+   Target T;
+   T.lx = (int)(code & 15u);
+   T.hr0 = (int)(code >> 9);
+   T.k = L.rowk[(code >> 4) & 31u] + tnum;
    return T;
 }
 
@@ -454,7 +528,7 @@ __device__ int choose_level(const DevParams& P, int X0, int Y0, int Z0, const ui
             for (int x = 0; x < TBX && fits; x += bx)
             {
                SubTile t = {X0 + x, Y0 + y, Z0 + z, bx, by, bz};
-               fits = halo_population(P, t, cell_start) <= cap;
+               fits = halo_population(P, t, cell_start) + 3 * (by + 2) * (bz + 2) <= cap;   // + row padding
             }
       if (fits)
          return level;
@@ -462,13 +536,11 @@ __device__ int choose_level(const DevParams& P, int X0, int Y0, int Z0, const ui
    return 4;
 }
 
-__device__ __forceinline__ void tile_origin(const DevParams& P, int& X0, int& Y0, int& Z0)
+__device__ __forceinline__ void tile_origin(int& X0, int& Y0, int& Z0)
 {
-   int tx = (P.fx + TBX - 1) / TBX, ty = (P.fy + TBY - 1) / TBY;
-   int b = blockIdx.x;
-   X0 = (b % tx) * TBX;
-   Y0 = ((b / tx) % ty) * TBY;
-   Z0 = (b / (tx * ty)) * TBZ;
+   X0 = blockIdx.x * TBX;     // 3D launch grid: no per-thread divisions
+   Y0 = blockIdx.y * TBY;
+   Z0 = blockIdx.z * TBZ;
 }
 
 // particles of the un-haloed tile (quick exit for empty space); warp 0
@@ -520,7 +592,7 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
    const float tmin = -1e-5f * P.hs2;         // enlarged radius: a superset of the exact d2 < h2 test
    for (int tnum = threadIdx.x; tnum < L.ntargets; tnum += blockDim.x)
    {
-      Target T = locate_target(t, L, tnum);
+      Target T = locate_target_search(t, L, tnum);
       const float4 pi = src[T.k + L.row_delta[T.hr0]];
       uint2* rec = hit_rec + stream_base(T.k);
       float sum = 0.0f;
@@ -581,6 +653,205 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
    }
 }
 
+// ---- packed density sweep (the staged path) -----------------------------------
+// Shared-memory layout: candidates in groups of four, structure of arrays inside the
+// group -- {x0 x1 x2 x3}{y0..y3}{z0..z3}[{m0..m3}] -- so that one LDS.128 per
+// coordinate feeds two packed instructions (candidates 0,1 and 2,3).  Staged index s
+// lives in group s >> 2, lane s & 3.  Equal masses (UMASS) drop the fourth row.
+template <bool UMASS>
+__device__ __forceinline__ void stage_rows_packed(const SubTile& t, const TileLayout& L,
+                                                  const float4* __restrict__ src, float* __restrict__ sg)
+{
+   constexpr int GF = UMASS ? 12 : 16;   // floats per group
+   const int rows = (t.by + 2) * (t.bz + 2);
+   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+   for (int hr = warp; hr < rows; hr += nwarps)
+   {
+      int g0 = L.row_g0[hr], len = L.row_len[hr], off = g0 + L.row_delta[hr];
+      for (int j = lane; j < len; j += 32)
+      {
+         float4 p = __ldg(&src[g0 + j]);
+         int s = off + j;
+         float* d = sg + (s >> 2) * GF + (s & 3);
+         d[0] = p.x;
+         d[4] = p.y;
+         d[8] = p.z;
+         if (!UMASS)
+            d[12] = p.w;
+      }
+      // runs are widened to whole groups: the unused lanes of the row's last group hold
+      // a position that is far from everything (and no mass)
+      int s = off + len + lane;
+      if (s < off + ((len + 3) & ~3))
+      {
+         float* d = sg + (s >> 2) * GF + (s & 3);
+         d[0] = 1e30f;
+         d[4] = 0.0f;
+         d[8] = 0.0f;
+         if (!UMASS)
+            d[12] = 0.0f;
+      }
+   }
+}
+
+// Per target: the 9 x-runs, widened to group boundaries, in chunks of 32 candidates
+// (8 groups).  With e = d2 * scale^2 - hs2 per candidate (two per instruction):
+//   hit bit = sign of (e - 1e-5 hs2): a superset of the exact d2 < h2 test, the force
+//             sweep applies the exact one to the survivors;
+//   poly6   : sum += min(e, 0)^3 = -(hs2 - d2)^3 inside the radius, 0 outside.
+// Rows start on group boundaries, so the candidates a widened run picks up outside its
+// three cells are particles of the SAME row two or more columns away (or sentinels):
+// they are masked out of the hit bits, and are at least h away, so their poly6 term is
+// 0 (or one ulp of nothing at exactly h).
+// Per pair of candidates: 1.5 LDS.128 + 9 packed FMA-pipe instructions + 2 FMNMX +
+// 2 SHF, against 2 x (1 + 9 + 1 + 1) for the scalar loop.
+// 128-bit shared-memory load at a compile-time byte offset from a shared-space address
+// (keeps the address arithmetic out of the unrolled groups: one register + immediate)
+template <int OFF>
+__device__ __forceinline__ ulonglong2 lds128(unsigned addr)
+{
+   ulonglong2 v;
+   asm volatile("ld.shared.v2.u64 {%0, %1}, [%2+%3];" : "=l"(v.x), "=l"(v.y) : "r"(addr), "n"(OFF));
+   return v;
+}
+
+// one group of four candidates (two packed pairs) of the density sweep; the group
+// starts OFF bytes from shared address `a`
+template <bool UNIT, bool UMASS, int OFF>
+__device__ __forceinline__ void density_group(unsigned a, f32x2 NX, f32x2 NY, f32x2 NZ, f32x2 NH, f32x2 NTHR,
+                                              f32x2 S2, unsigned& mask, f32x2& sum2)
+{
+   const ulonglong2 X = lds128<OFF>(a), Y = lds128<OFF + 16>(a), Z = lds128<OFF + 32>(a);
+   ulonglong2 M;
+   if (!UMASS)
+      M = lds128<OFF + 48>(a);
+#pragma unroll
+   for (int half = 0; half < 2; half++)
+   {
+      f32x2 dx = fadd2(half ? X.y : X.x, NX);
+      f32x2 dy = fadd2(half ? Y.y : Y.x, NY);
+      f32x2 dz = fadd2(half ? Z.y : Z.x, NZ);
+      f32x2 ee;
+      if (UNIT)
+         ee = ffma2(dz, dz, ffma2(dy, dy, ffma2(dx, dx, NH)));
+      else
+         ee = ffma2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))), S2, NH);
+      float s0, s1, e0, e1;
+      unpack2(fadd2(ee, NTHR), s0, s1);
+      mask = __funnelshift_l(__float_as_uint(s0), mask, 1);
+      mask = __funnelshift_l(__float_as_uint(s1), mask, 1);
+      unpack2(ee, e0, e1);
+      f32x2 u = pack2(fminf(e0, 0.0f), fminf(e1, 0.0f));
+      if (UMASS)
+         sum2 = ffma2(fmul2(u, u), u, sum2);
+      else
+         sum2 = ffma2(fmul2(half ? M.y : M.x, u), fmul2(u, u), sum2);
+   }
+}
+
+template <bool UNIT, bool UMASS>
+__device__ __forceinline__ void density_targets_packed(const DevParams& P, const SubTile& t, const TileLayout& L,
+                                                       const float* __restrict__ sg,
+                                                       const float4* __restrict__ s_pos4,
+                                                       const uint32_t* __restrict__ idx_sorted,
+                                                       const float4* __restrict__ vel4, float4* __restrict__ s_posA4,
+                                                       float4* __restrict__ s_velB4, float* __restrict__ s_rho,
+                                                       uint2* __restrict__ hit_rec, unsigned* __restrict__ hit_info)
+{
+   constexpr int GF = UMASS ? 12 : 16;   // floats per group
+   const float scale2 = P.scale * P.scale;
+   const float thr = 1e-5f * P.hs2;
+   const f32x2 NH = pack2(-P.hs2, -P.hs2), NTHR = pack2(-thr, -thr), S2 = pack2(scale2, scale2);
+   const unsigned sbase = (unsigned)__cvta_generic_to_shared(sg);
+   const int rowstep = t.by + 2;
+   for (int tnum = threadIdx.x; tnum < L.ntargets; tnum += blockDim.x)
+   {
+      Target T = locate_target(L, tnum);
+      const float4 pi = __ldg(&s_pos4[T.k]);
+      const f32x2 NX = pack2(-pi.x, -pi.x), NY = pack2(-pi.y, -pi.y), NZ = pack2(-pi.z, -pi.z);
+      uint2* rec = hit_rec + stream_base(T.k);
+      f32x2 sum2 = pack2(0.0f, 0.0f);
+      int nw = 0, nhits = 0;
+      // the 9 runs in ascending row order: (z-1: y-1, y, y+1), (z: ...), (z+1: ...)
+      const int* csp = &L.cs[T.hr0 - rowstep - 1][T.lx - 1];
+      const int* dlp = &L.row_delta[T.hr0 - rowstep - 1];
+#pragma unroll 1
+      for (int r = 0; r < 9; r++)
+      {
+         const int delta = dlp[0];
+         const int b = csp[0] + delta;
+         const int e = csp[3] + delta;
+         const bool last_of_plane = (r == 2 || r == 5);
+         csp += last_of_plane ? (rowstep - 2) * CSW : CSW;
+         dlp += last_of_plane ? rowstep - 2 : 1;
+#pragma unroll 1
+         for (int c0 = b & ~3; c0 < e; c0 += 32)
+         {
+            const int ng = min(8, (e - c0 + 3) >> 2);
+            const unsigned a0 = sbase + (unsigned)((c0 >> 2) * (GF * 4));   // the chunk's first group
+            // one hit bit per candidate, shifted in at the LSB: after the chunk candidate i
+            // sits at bit 31 - i.  Nested ifs instead of a loop: no bookkeeping, lanes with
+            // fewer groups drop out and the warp reconverges once (a fall-through switch
+            // would serialise the lanes by entry point).
+            unsigned mask = 0;
+#define SPH_GROUP(N) density_group<UNIT, UMASS, (N) * GF * 4>(a0, NX, NY, NZ, NH, NTHR, S2, mask, sum2)
+            SPH_GROUP(0);
+            if (ng > 1)
+            {
+               SPH_GROUP(1);
+               if (ng > 2)
+               {
+                  SPH_GROUP(2);
+                  if (ng > 3)
+                  {
+                     SPH_GROUP(3);
+                     if (ng > 4)
+                     {
+                        SPH_GROUP(4);
+                        if (ng > 5)
+                        {
+                           SPH_GROUP(5);
+                           if (ng > 6)
+                           {
+                              SPH_GROUP(6);
+                              if (ng > 7)
+                                 SPH_GROUP(7);
+                           }
+                        }
+                     }
+                  }
+               }
+            }
+#undef SPH_GROUP
+            mask <<= 32 - 4 * ng;
+            // keep the candidates of the run proper: [b, e)
+            const int lo = b - c0, hi = e - c0;
+            if (lo > 0)
+               mask &= 0xffffffffu >> lo;
+            if (hi < 32)
+               mask &= ~(0xffffffffu >> hi);
+            if (mask != 0u)
+            {
+               if (nw < WCAP)
+                  rec[(size_t)nw * 32] = make_uint2(mask, (unsigned)(c0 - delta));
+               nw++;
+               nhits += __popc(mask);
+            }
+         }
+      }
+      hit_info[T.k] = nw <= WCAP ? ((unsigned)nw | ((unsigned)nhits << 8)) : kNoStream;
+      float sa, sb;
+      unpack2(sum2, sa, sb);
+      const float sum = -(sa + sb);
+      // the particle itself sat in the centre run with e = -hs2: remove its own term (the
+      // reference skips realIndex == particleIndex, sph.cpp:737); a NaN position has term 0
+      float t_self = (pi.x == pi.x && pi.y == pi.y && pi.z == pi.z) ? P.hs2 : 0.0f;
+      float self = UMASS ? (t_self * t_self) * t_self : __fmul_rn(pi.w * t_self, t_self * t_self);
+      float rho = UMASS ? (P.k1 * pi.w) * (sum - self) : P.k1 * (sum - self);
+      density_store(P, T.k, pi, rho, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
+   }
+}
+
 template <bool UNIT, bool UMASS>
 __global__ void __launch_bounds__(kTileThreads, 2)
    k_density_tiled(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ cell_start,
@@ -589,15 +860,15 @@ __global__ void __launch_bounds__(kTileThreads, 2)
                    uint2* __restrict__ hit_rec, unsigned* __restrict__ hit_info)
 {
    extern __shared__ __align__(16) unsigned char smem_raw[];
-   float4* sp = reinterpret_cast<float4*>(smem_raw);
+   float* sg = reinterpret_cast<float*>(smem_raw);
    __shared__ TileLayout L;
    __shared__ int s_level, s_pop;
    int X0, Y0, Z0;
-   tile_origin(P, X0, Y0, Z0);
+   tile_origin(X0, Y0, Z0);
    if (threadIdx.x < 32)
    {
       int pop = tile_population(P, X0, Y0, Z0, cell_start);
-      int level = pop > 0 ? choose_level(P, X0, Y0, Z0, cell_start, kCap) : 0;
+      int level = pop > 0 ? choose_level(P, X0, Y0, Z0, cell_start, UMASS ? kCap : kCapMass) : 0;
       if (threadIdx.x == 0)
       {
          s_pop = pop;
@@ -621,10 +892,10 @@ __global__ void __launch_bounds__(kTileThreads, 2)
             {
                if (level < 4)
                {
-                  stage_rows(t, L, s_pos4, sp);
+                  stage_rows_packed<UMASS>(t, L, s_pos4, sg);
                   __syncthreads();
-                  density_targets<true, UNIT, UMASS>(P, t, L, sp, idx_sorted, vel4, s_posA4, s_velB4, s_rho, hit_rec,
-                                                     hit_info);
+                  density_targets_packed<UNIT, UMASS>(P, t, L, sg, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho,
+                                                      hit_rec, hit_info);
                }
                else
                   density_targets<false, UNIT, UMASS>(P, t, L, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho,
@@ -807,7 +1078,8 @@ __global__ void __launch_bounds__(kFlatThreads)
    nbr_count[o] = s_count[k];
 }
 
-size_t density_smem() { return sizeof(float4) * (size_t)kCap; }
+size_t density_smem() { return 12 * (size_t)(kCap + 4); }   // == 16 * (kCapMass + 4) rounded up
+static_assert(16 * (kCapMass + 4) <= 12 * (kCap + 4), "both layouts share one shared-memory size");
 
 
 }  // namespace
@@ -853,7 +1125,7 @@ int sph_step_full(sphb200_ctx* ctx)
    const bool tiled = ctx->params.kernel_variant != 1;
    if (tiled)
    {
-      int tiles = ((P.fx + TBX - 1) / TBX) * ((P.fy + TBY - 1) / TBY) * ((P.fz + TBZ - 1) / TBZ);   // local grid
+      dim3 tiles((P.fx + TBX - 1) / TBX, (P.fy + TBY - 1) / TBY, (P.fz + TBZ - 1) / TBZ);   // local grid
       auto kd = k_density_tiled<false, false>;
       if (P.scale == 1.0f)
          kd = ctx->uniform_mass ? k_density_tiled<true, true> : k_density_tiled<true, false>;

@@ -295,25 +295,31 @@ def test_full_tiny_and_empty_systems():
 
 
 def test_full_tiled_equals_flat_bitwise_on_integers_and_close_on_fields():
+    """The tiled sweep (packed FP32, two partial sums) and the flat one (scalar, one sum) are two
+    equally valid FP32 evaluation orders of the same neighbour sets."""
     cfg = scenes.CONFIGS["dambreak_128k"]
     nx, ny, nz = cfg["sites"]
     n = nx * ny * nz
-    pos = scenes.lattice_scene(nx, ny, nz, scenes.lattice_spacing(0.1, 60))   # denser: ~60 neighbours
     vel = np.zeros((n, 3), np.float32)
-    out = []
-    for variant in (0, 1):
-        sph = S.SPH(_full_params(cfg, n, 160, variant), init_scene=False)
-        sph.upload(pos, vel)
-        sph.step_n(3)
-        out.append((sph.download(F.NEIGHBOR_COUNT), sph.download(F.DENSITY), sph.download(F.POSITION),
-                    sph.energies()))
-        sph.close()
-    assert np.array_equal(out[0][0], out[1][0])
-    # three steps of two different (equally valid) FP32 evaluation orders: rounding-level
-    # differences of the state feed back into the density
-    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-4)
-    np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-5, atol=1e-5)
-    np.testing.assert_allclose(out[0][3], out[1][3], rtol=1e-5)
+    # (~neighbours, steps): the dense lattice is far from rest (rho >> rho0, accelerations on the CFL
+    # clamp), so rounding-level density differences are amplified from the second step on: compare it
+    # after one step, and the rest-density lattice after three
+    for nu, steps in ((60, 1), (40, 3)):
+        pos = scenes.lattice_scene(nx, ny, nz, scenes.lattice_spacing(0.1, nu))
+        out = []
+        for variant in (0, 1):
+            sph = S.SPH(_full_params(cfg, n, 160, variant), init_scene=False)
+            sph.upload(pos, vel)
+            sph.step_n(steps)
+            out.append((sph.download(F.NEIGHBOR_COUNT), sph.download(F.DENSITY), sph.download(F.POSITION),
+                        sph.energies()))
+            sph.close()
+        assert np.array_equal(out[0][0], out[1][0])
+        assert out[0][0].mean() > 0.7 * nu
+        np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-5)
+        np.testing.assert_allclose(out[0][2], out[1][2], rtol=1e-5, atol=1e-5)
+        # far-from-rest lattice: 1/p_i amplifies the last bit of rho_i where p_i ~ 0 (see well_conditioned)
+        np.testing.assert_allclose(out[0][3], out[1][3], rtol=1e-5 if nu == 40 else 1e-3)
 
 
 # ------------------------------------------------------------------ ABI errors
