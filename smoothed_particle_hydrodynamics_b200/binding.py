@@ -101,7 +101,8 @@ API = [
 
 
 def lib_path():
-    return os.path.join(_HERE, "libsphb200.so")
+    # SPHB200_LIB: an alternative build of the same library (tools/build_variant.py, A/B timing only)
+    return os.environ.get("SPHB200_LIB") or os.path.join(_HERE, "libsphb200.so")
 
 
 _lib = None

@@ -27,13 +27,31 @@
 namespace
 {
 
-constexpr int TBX = 8, TBY = 8, TBZ = 4;    // tile extent in fine cells (x rows are contiguous in memory)
+// Tile shape, CTA size and staging capacity.  Overridable at compile time for A/B runs
+// (tools/build_variant.py); the defaults are the measured best (profiles/r01_history.md).
+#ifndef SPH_TBY
+#define SPH_TBY 8
+#endif
+#ifndef SPH_TBZ
+#define SPH_TBZ 4
+#endif
+#ifndef SPH_TILE_THREADS
+#define SPH_TILE_THREADS 512
+#endif
+#ifndef SPH_TILE_CTAS
+#define SPH_TILE_CTAS 2
+#endif
+#ifndef SPH_CAP
+#define SPH_CAP 6600
+#endif
+constexpr int TBX = 8, TBY = SPH_TBY, TBZ = SPH_TBZ;   // tile extent in fine cells (x rows are contiguous in memory)
 constexpr int HROWS = (TBY + 2) * (TBZ + 2);   // halo rows (y,z) of a full tile
 constexpr int CSW = TBX + 3;                // cell_start entries per halo row
 constexpr int TROWS = TBY * TBZ;            // target rows of a full tile (<= 32: one warp scans them)
-constexpr int kTileThreads = 512;
-constexpr int kCap = 6600;                  // staged particles per (sub-)tile, equal masses (12 B each)
-constexpr int kCapMass = 4948;              // ... with per-particle masses (16 B each): same 79 KB, 2 CTAs per SM
+constexpr int kTileThreads = SPH_TILE_THREADS;
+constexpr int kTileCtas = SPH_TILE_CTAS;    // resident CTAs per SM the kernel is built for
+constexpr int kCap = SPH_CAP;               // staged particles per (sub-)tile, equal masses (12 B each)
+constexpr int kCapMass = (12 * (kCap + 4)) / 16 - 4;   // ... with per-particle masses (16 B each): same bytes
 constexpr int WCAP = 32;                    // hit-mask records per particle (32 candidates each)
 constexpr unsigned kNoStream = 0xffu;       // info.nw value: no stream, scan instead
 constexpr int RSM = 16;                     // records per thread kept in shared memory by the force sweep
@@ -461,20 +479,6 @@ __device__ void setup_layout(const DevParams& P, const SubTile& t, const uint32_
    __syncthreads();
 }
 
-// copies the halo rows of `src` (global, cell-sorted) into shared memory
-__device__ __forceinline__ void stage_rows(const SubTile& t, const TileLayout& L, const float4* __restrict__ src,
-                                           float4* __restrict__ dst)
-{
-   const int rows = (t.by + 2) * (t.bz + 2);
-   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-   for (int hr = warp; hr < rows; hr += nwarps)
-   {
-      int g0 = L.row_g0[hr], len = L.row_len[hr], off = g0 + L.row_delta[hr];
-      for (int j = lane; j < len; j += 32)
-         dst[off + j] = __ldg(&src[g0 + j]);
-   }
-}
-
 struct Target
 {
    int k;        // global sorted index
@@ -824,12 +828,10 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
             }
 #undef SPH_GROUP
             mask <<= 32 - 4 * ng;
-            // keep the candidates of the run proper: [b, e)
-            const int lo = b - c0, hi = e - c0;
-            if (lo > 0)
-               mask &= 0xffffffffu >> lo;
-            if (hi < 32)
-               mask &= ~(0xffffffffu >> hi);
+            // keep the candidates of the run proper, [b, e): clear the first b - c0 bits (first
+            // chunk only) and everything past bit e - c0 (last chunk only; the clamped funnel
+            // shift yields the top min(e - c0, 32) bits)
+            mask &= (0xffffffffu >> max(b - c0, 0)) & __funnelshift_rc(0u, 0xffffffffu, e - c0);
             if (mask != 0u)
             {
                if (nw < WCAP)
@@ -853,7 +855,7 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
 }
 
 template <bool UNIT, bool UMASS>
-__global__ void __launch_bounds__(kTileThreads, 2)
+__global__ void __launch_bounds__(kTileThreads, kTileCtas)
    k_density_tiled(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ cell_start,
                    const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ vel4,
                    float4* __restrict__ s_posA4, float4* __restrict__ s_velB4, float* __restrict__ s_rho,

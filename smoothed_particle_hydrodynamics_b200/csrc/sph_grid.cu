@@ -1,11 +1,21 @@
-// sph_grid.cu -- voxel binning, device radix sort, cell tables, cell-order gather.
+// sph_grid.cu -- voxel binning, counting sort into cell order, cell tables, gather.
 //
 // Replaces clearGrid + voxelizeParticles (sph.cpp:429-481): instead of
-// QList::push_back per particle, particles get a cell key, are stably sorted by
-// it FROM ORIGINAL-INDEX ORDER every step (so the order inside a cell is
-// ascending particle index == the reference's push_back order, sph.cpp:476-480)
-// and an exclusive-scan table cell_start[c] .. cell_start[c+1] replaces the lists.
+// QList::push_back per particle, particles get a cell key and are counting-sorted
+// by it every step; an exclusive-scan table cell_start[c] .. cell_start[c+1]
+// replaces the lists.  The order inside a cell is ascending particle index == the
+// reference's push_back order (sph.cpp:476-480): the histogram atomics hand out
+// arbitrary slots, and the gather pass re-ranks the (few) members of each cell.
+//   k_cell_keys   : key + histogram atomic (returns the particle's slot in its cell)
+//   scan          : cell_start = exclusive sum of the histogram (cub::DeviceScan)
+//   k_scatter     : particle -> cell_start[key] + slot
+//   k_rank_gather : rank inside the cell by particle index (global id in slab mode),
+//                   final index order + positions gathered into cell order
+// ~100 B of traffic per particle in four streaming passes instead of a 3-pass radix
+// sort of (key, index) pairs plus a gather (0.73 -> 0.4 ms at 16.7M particles).
 #include <cub/cub.cuh>
+
+#include <cstdlib>
 
 #include "sph_math.cuh"
 
@@ -24,6 +34,7 @@ template <bool FINE>
 __global__ void __launch_bounds__(kThreads) k_cell_keys(DevParams P, int cells, const float4* __restrict__ pos4,
                                                          uint32_t* __restrict__ keys,
                                                          uint32_t* __restrict__ cell_count,
+                                                         uint32_t* __restrict__ cell_slot,
                                                          int* __restrict__ voxel_id_out)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -32,7 +43,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(DevParams P, int cells, 
    if (P.slab && P.slot_state[i] == SLOT_FREE)
    {
       keys[i] = (uint32_t)cells;
-      atomicAdd(&cell_count[cells], 1u);
+      cell_slot[i] = atomicAdd(&cell_count[cells], 1u);
       return;
    }
    float4 p = pos4[i];
@@ -55,7 +66,65 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(DevParams P, int cells, 
    keys[i] = key;
    if (voxel_id_out)
       voxel_id_out[i] = sph_voxel_id(vx, vy, vz, P.gx, P.gy);   // global voxel id, as the reference numbers it
-   atomicAdd(&cell_count[key], 1u);
+   cell_slot[i] = atomicAdd(&cell_count[key], 1u);
+}
+
+// counting-sort scatter: particle i goes to position cell_start[key] + slot.  The
+// slot order inside a cell is whatever the atomics produced; `ord` carries the value
+// the members are ranked by afterwards (particle index, or global id in slab mode).
+__global__ void __launch_bounds__(kThreads) k_scatter(int n, const uint32_t* __restrict__ keys,
+                                                       const uint32_t* __restrict__ cell_slot,
+                                                       const uint32_t* __restrict__ cell_start,
+                                                       const uint32_t* __restrict__ gid,
+                                                       uint32_t* __restrict__ keys_sorted,
+                                                       uint32_t* __restrict__ tmp_ord, uint32_t* __restrict__ tmp_idx)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n)
+      return;
+   uint32_t key = keys[i];
+   uint32_t p = __ldg(&cell_start[key]) + cell_slot[i];
+   keys_sorted[p] = key;
+   if (gid)
+   {
+      tmp_ord[p] = gid[i];
+      tmp_idx[p] = (uint32_t)i;
+   }
+   else
+      tmp_ord[p] = (uint32_t)i;
+}
+
+// One thread per sorted position: rank of its particle among the members of its cell
+// (cells hold ~8 particles and the members sit in consecutive, L1-resident words), then
+// the final index order and -- FULL mode -- the position gathered into cell order.
+// Free slots (slab mode, sentinel cell `cells`) keep their arbitrary order.
+template <bool GATHER>
+__global__ void __launch_bounds__(kThreads) k_rank_gather(int n, int cells, const uint32_t* __restrict__ keys_sorted,
+                                                           const uint32_t* __restrict__ cell_start,
+                                                           const uint32_t* __restrict__ tmp_ord,
+                                                           const uint32_t* __restrict__ tmp_idx,
+                                                           const float4* __restrict__ pos4,
+                                                           uint32_t* __restrict__ idx_sorted,
+                                                           float4* __restrict__ s_pos4)
+{
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k >= n)
+      return;
+   const uint32_t c = keys_sorted[k];
+   const uint32_t mine = tmp_ord[k];
+   const uint32_t me = tmp_idx ? tmp_idx[k] : mine;
+   if ((int)c >= cells)
+   {
+      idx_sorted[k] = me;
+      return;
+   }
+   const int s = (int)__ldg(&cell_start[c]), e = (int)__ldg(&cell_start[c + 1]);
+   int rank = 0;
+   for (int a = s; a < e; a++)
+      rank += (tmp_ord[a] < mine) ? 1 : 0;
+   idx_sorted[s + rank] = me;
+   if (GATHER)
+      s_pos4[s + rank] = __ldg(&pos4[me]);
 }
 
 __global__ void __launch_bounds__(kThreads) k_iota(uint32_t* a, int n)
@@ -191,10 +260,10 @@ int sph_bin_and_sort(sphb200_ctx* ctx, bool fine)
    {
       if (fine)
          k_cell_keys<true><<<blocks_for(n), kThreads, 0, st>>>(P, cells, ctx->pos4, ctx->keys, ctx->cell_count,
-                                                               ctx->voxel_id);
+                                                               ctx->cell_slot, ctx->voxel_id);
       else
          k_cell_keys<false><<<blocks_for(n), kThreads, 0, st>>>(P, cells, ctx->pos4, ctx->keys, ctx->cell_count,
-                                                                ctx->voxel_id);
+                                                                ctx->cell_slot, ctx->voxel_id);
       ctx->launches++;
       SPH_CUDA_CHECK(ctx, cudaGetLastError());
       ctx->voxel_ids_valid = true;
@@ -204,8 +273,25 @@ int sph_bin_and_sort(sphb200_ctx* ctx, bool fine)
                                                      st));
    ctx->launches += 2;
    ctx->idx_order = ctx->idx_sorted;
-   if (n > 0)
+   if (n > 0 && !ctx->use_radix_sort)
    {
+      const uint32_t* gid = ctx->comm ? ctx->gid : nullptr;
+      k_scatter<<<blocks_for(n), kThreads, 0, st>>>(n, ctx->keys, ctx->cell_slot, ctx->cell_start, gid,
+                                                    ctx->keys_sorted, ctx->tmp_ord, ctx->tmp_idx);
+      if (fine)
+         k_rank_gather<true><<<blocks_for(n), kThreads, 0, st>>>(n, cells, ctx->keys_sorted, ctx->cell_start,
+                                                                 ctx->tmp_ord, gid ? ctx->tmp_idx : nullptr,
+                                                                 ctx->pos4, ctx->idx_sorted, ctx->s_pos4);
+      else
+         k_rank_gather<false><<<blocks_for(n), kThreads, 0, st>>>(n, cells, ctx->keys_sorted, ctx->cell_start,
+                                                                  ctx->tmp_ord, gid ? ctx->tmp_idx : nullptr,
+                                                                  ctx->pos4, ctx->idx_sorted, ctx->s_pos4);
+      ctx->launches += 2;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   }
+   else if (n > 0)
+   {
+      // A/B path (SPHB200_RADIX_SORT=1): stable radix sort of (key, index) from index order
       int bits = 1;
       while (bits < 32 && (1ll << bits) < (long long)cells + (ctx->comm ? 1 : 0))
          bits++;
@@ -243,6 +329,12 @@ int sph_grid_alloc(sphb200_ctx* ctx)
                                    (uint32_t*)nullptr, ctx->capacity > 0 ? ctx->capacity : 1, 0, 32);
    ctx->cub_temp_bytes = (t_scan > t_sort ? t_scan : t_sort) + 256;
    SPH_CUDA_CHECK(ctx, cudaMalloc(&ctx->cub_temp, ctx->cub_temp_bytes));
+   size_t slots = (size_t)(ctx->capacity > 0 ? ctx->capacity : 1);
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->cell_slot, sizeof(uint32_t) * slots));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->tmp_ord, sizeof(uint32_t) * slots));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->tmp_idx, sizeof(uint32_t) * slots));
+   const char* radix = getenv("SPHB200_RADIX_SORT");
+   ctx->use_radix_sort = radix && radix[0] == '1';
    return SPHB200_OK;
 }
 
@@ -251,7 +343,11 @@ void sph_grid_free(sphb200_ctx* ctx)
    if (ctx->cell_count) cudaFree(ctx->cell_count);
    if (ctx->cell_start) cudaFree(ctx->cell_start);
    if (ctx->cub_temp) cudaFree(ctx->cub_temp);
+   if (ctx->cell_slot) cudaFree(ctx->cell_slot);
+   if (ctx->tmp_ord) cudaFree(ctx->tmp_ord);
+   if (ctx->tmp_idx) cudaFree(ctx->tmp_idx);
    ctx->cell_count = ctx->cell_start = nullptr;
+   ctx->cell_slot = ctx->tmp_ord = ctx->tmp_idx = nullptr;
    ctx->cub_temp = nullptr;
 }
 

@@ -87,6 +87,9 @@ struct sphb200_ctx
    // per-step scratch
    uint32_t *keys, *keys_sorted, *idx_iota, *idx_sorted;
    const uint32_t* idx_order;   // particle order of the last binning: idx_sorted, or idx_fixed in slab mode
+   uint32_t* cell_slot;   // per particle: its slot inside its cell (return value of the histogram atomic)
+   uint32_t *tmp_ord, *tmp_idx;   // counting-sort scatter output: ranking value / particle index per position
+   bool use_radix_sort;   // A/B switch (env SPHB200_RADIX_SORT=1): CUB radix sort instead of the counting sort
    uint32_t* cell_count;  // histogram, cells_alloc + 1
    uint32_t* cell_start;  // exclusive scan, cells_alloc + 1
    float4* s_pos4;        // sorted snapshot (x,y,z,m)
