@@ -15,7 +15,7 @@ north-star target is quoted on.  N>1: 16M per GPU box-drop, z-slab decomposition
 `e2e`     : the same metric through sphb200_step_host with PINNED HOST buffers:
             H2D of positions/velocities/masses + step + D2H of new positions /
             velocities inside the timed region, every step.
-`roofline`: dominant kernel (force+integrate sweep), algorithmic bytes / its
+`roofline`: dominant kernel (decided live: force or density sweep), algorithmic bytes / its
             CUDA-event duration vs the measured HBM copy bandwidth.
 `cpu_baseline` / `--impl reference`: the UNMODIFIED reference physics compiled in
             place (oracle/_ref, timing build, 1 thread -- the reference has no
@@ -39,9 +39,9 @@ from oracle import scenes  # noqa: E402  (input synthesis only)
 ALG_BYTES_STEP = 240.0     # algorithmic bytes per particle-step (whole pipeline)
 ALG_BYTES_FORCE = 72.0     # force+integrate+collide sweep: R(16+16+4) + W(16+16) + R4
 ALG_BYTES_DENSITY = 20.0   # density+EOS sweep: R16 + W4
-# dram__bytes_read.sum + dram__bytes_write.sum of k_density_tiled per launch at 16.7M particles,
-# from the committed `ncu --set full` capture (profiles/r01_ncu_top_kernels_16m.csv)
-NCU_TRAFFIC_DENSITY_16M = 0.848093e9 + 1.528132e9
+# dram__bytes_read.sum + dram__bytes_write.sum per launch at 16.7M particles, from the committed
+# `ncu --set full` capture (profiles/r01_ncu_top_kernels_16m.csv)
+NCU_TRAFFIC_16M = {"density": 0.815e9 + 1.525e9, "force": 1.979e9 + 0.853e9}
 NU = 40.0
 
 
@@ -283,7 +283,18 @@ def run_ours(args):
     dens_ms, force_ms = float(phase[2]), float(phase[4])
     hbm, peak_kind = measured_peaks()
     n_dev = n
-    achieved = ALG_BYTES_DENSITY * n_dev / (dens_ms * 1e-3) / 1e9 if dens_ms > 0 else 0.0
+    # the dominant kernel of the step, decided live: the force sweep or the density sweep
+    if force_ms >= dens_ms:
+        dom = {"key": "force", "ms": force_ms, "bytes": ALG_BYTES_FORCE,
+               "kernel": "k_force_stream (pressure + viscosity + integrate + walls, hit-mask stream driven)",
+               "note": "bound by L1 wavefronts of the scattered 16-byte neighbour gathers (ncu: "
+                       "l1tex__data_pipe_lsu_wavefronts 90%, DRAM 14% busy), not by HBM: DESIGN.md section 5"}
+    else:
+        dom = {"key": "density", "ms": dens_ms, "bytes": ALG_BYTES_DENSITY,
+               "kernel": "k_density_tiled (density + EOS + hit-mask stream sweep, packed FP32)",
+               "note": "FP32 pipe / issue bound (ncu: FMA pipe 57% of active cycles at 2 cycles per packed "
+                       "instruction, DRAM 6% busy), not HBM bound: DESIGN.md section 5"}
+    achieved = dom["bytes"] * n_dev / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
 
     # ---- end to end through host buffers -------------------------------------
     # every step: H2D of positions / velocities / masses (/ ids) from pinned memory,
@@ -333,13 +344,13 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "particle-updates/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_density_tiled (density + EOS + hit-mask stream sweep)",
+        "roofline": {"bound": "hbm", "kernel": dom["kernel"],
                      "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
-                     "traffic": NCU_TRAFFIC_DENSITY_16M if (n_dev == 16777216 and NU == 40.0) else None,
+                     "traffic": NCU_TRAFFIC_16M[dom["key"]] if (n_dev == 16777216 and NU == 40.0) else None,
                      "traffic_unit": "bytes per launch (ncu dram read+write, profiles/r01_ncu_top_kernels_16m.csv)",
-                     "peak_kind": peak_kind, "alg_bytes_per_particle": ALG_BYTES_DENSITY, "kernel_ms": dens_ms,
-                     "note": "instruction-issue bound (ncu: 82% issue slots busy, DRAM 9% busy), not HBM bound: "
-                             "DESIGN.md section 5"},
+                     "peak_kind": peak_kind, "alg_bytes_per_particle": dom["bytes"], "kernel_ms": dom["ms"],
+                     "other_kernel_ms": {"density": dens_ms, "force": force_ms},
+                     "note": dom["note"]},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference_sample(steps=10, warmup=1)

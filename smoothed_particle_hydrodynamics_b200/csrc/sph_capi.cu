@@ -23,12 +23,14 @@ constexpr int kThreads = 256;
 __global__ void __launch_bounds__(kThreads) k_pack_state(int n, const float* __restrict__ pos_xyz,
                                                           const float* __restrict__ vel_xyz,
                                                           const float* __restrict__ mass, float4* __restrict__ pos4,
-                                                          float4* __restrict__ vel4)
+                                                          float4* __restrict__ vel4, int* __restrict__ mass_differs)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n)
       return;
    float m = mass ? mass[i] : 1.0f;
+   if (mass && m != mass[0])
+      *mass_differs = 1;      // benign race: every writer stores the same value
    pos4[i] = make_float4(pos_xyz[3 * (size_t)i], pos_xyz[3 * (size_t)i + 1], pos_xyz[3 * (size_t)i + 2], m);
    vel4[i] = make_float4(vel_xyz[3 * (size_t)i], vel_xyz[3 * (size_t)i + 1], vel_xyz[3 * (size_t)i + 2], 0.0f);
 }
@@ -400,17 +402,22 @@ int sphb200_upload_state(sphb200_ctx* ctx, const float* pos_xyz, const float* ve
       SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(d_vel, vel_xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
       if (mass)
          SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->stage_f, mass, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+      int* d_flag = &ctx->d_scalars->overflow;   // free between steps (reset at the start of every step)
+      SPH_CUDA_CHECK(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
       k_pack_state<<<blocks_for(n), kThreads, 0, st>>>(n, d_pos, d_vel, mass ? ctx->stage_f : nullptr, ctx->pos4,
-                                                       ctx->vel4);
+                                                       ctx->vel4, d_flag);
       ctx->launches++;
       SPH_CUDA_CHECK(ctx, cudaGetLastError());
+      // all masses equal (the reference never sets anything but 1, sph.cpp:88): lets the
+      // density sweep factor the mass out of its inner loop.  Checked on the device while
+      // packing (a host loop over 16.7M masses cost more than the whole step).
+      int differs = 0;
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(&differs, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+      ctx->uniform_mass = differs == 0;
    }
-   // all masses equal (the reference never sets anything but 1, sph.cpp:88): lets the
-   // density sweep factor the mass out of its inner loop
-   ctx->uniform_mass = true;
-   if (mass)
-      for (int i = 1; i < n && ctx->uniform_mass; i++)
-         ctx->uniform_mass = mass[i] == mass[0];
+   else
+      ctx->uniform_mass = true;
    ctx->n_local = ctx->n_owned = n;
    ctx->lists_valid = false;
    ctx->snapshot_valid = false;

@@ -149,6 +149,43 @@ __global__ void k_mix(float* out, float a, float b, long long* cyc)
    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// packed and scalar FMAs interleaved (NP packed + NS scalar independent chains): do they
+// share one pipe, or does the scalar stream find a second one?
+template <int NP, int NS>
+__global__ void k_both(float* out, float a, float b, long long* cyc)
+{
+   u64 x[NP + 1];
+   float y[NS + 1];
+   u64 A = pack2(a, a), B = pack2(b, b);
+#pragma unroll
+   for (int i = 0; i < NP; i++) x[i] = pack2(threadIdx.x + i, i);
+#pragma unroll
+   for (int i = 0; i < NS; i++) y[i] = threadIdx.x - i;
+   long long t0 = clock64();
+   for (int it = 0; it < ITERS; it++)
+   {
+#pragma unroll
+      for (int i = 0; i < (NP > NS ? NP : NS); i++)
+      {
+         if (i < NP) x[i] = ffma2(x[i], A, B);
+         if (i < NS) y[i] = fmaf(y[i], a, b);
+      }
+   }
+   long long t1 = clock64();
+   float s = 0;
+#pragma unroll
+   for (int i = 0; i < NP; i++)
+   {
+      float lo, hi;
+      unpack2(x[i], lo, hi);
+      s += lo + hi;
+   }
+#pragma unroll
+   for (int i = 0; i < NS; i++) s += y[i];
+   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 // ---- density inner loops over shared memory ------------------------------------
 constexpr int NC = 2048;   // candidates staged
 constexpr int RUN = 256;   // candidates per thread and pass
@@ -306,6 +343,26 @@ int main()
       cudaDeviceSynchronize();
       c = avg_cycles(cyc, blocks);
       if (rep) printf("MIX    : %.3f trips/clk/SM (1 FFMA2 + 2 FMNMX + 2 SHF per trip)\n", warps_per_sm * ITERS * CH / c);
+      k_both<4, 4><<<blocks, threads>>>(out, 1.0001f, 0.5f, cyc);
+      cudaDeviceSynchronize();
+      c = avg_cycles(cyc, blocks);
+      if (rep) printf("4 FFMA2 + 4 FFMA : %.3f FMA-lane-equivalents/clk/SM (x32 lanes)\n", warps_per_sm * ITERS * (4 * 2 + 4) / c);
+      k_both<4, 2><<<blocks, threads>>>(out, 1.0001f, 0.5f, cyc);
+      cudaDeviceSynchronize();
+      c = avg_cycles(cyc, blocks);
+      if (rep) printf("4 FFMA2 + 2 FFMA : %.3f FMA-lane-equivalents/clk/SM\n", warps_per_sm * ITERS * (4 * 2 + 2) / c);
+      k_both<6, 2><<<blocks, threads>>>(out, 1.0001f, 0.5f, cyc);
+      cudaDeviceSynchronize();
+      c = avg_cycles(cyc, blocks);
+      if (rep) printf("6 FFMA2 + 2 FFMA : %.3f FMA-lane-equivalents/clk/SM\n", warps_per_sm * ITERS * (6 * 2 + 2) / c);
+      k_both<8, 0><<<blocks, threads>>>(out, 1.0001f, 0.5f, cyc);
+      cudaDeviceSynchronize();
+      c = avg_cycles(cyc, blocks);
+      if (rep) printf("8 FFMA2          : %.3f FMA-lane-equivalents/clk/SM\n", warps_per_sm * ITERS * (8 * 2) / c);
+      k_both<0, 8><<<blocks, threads>>>(out, 1.0001f, 0.5f, cyc);
+      cudaDeviceSynchronize();
+      c = avg_cycles(cyc, blocks);
+      if (rep) printf("8 FFMA           : %.3f FMA-lane-equivalents/clk/SM\n", warps_per_sm * ITERS * 8 / c);
       const int reps = 64;
       k_density_scalar<<<blocks, threads>>>(out, mout, 0.01f, cyc, reps);
       cudaDeviceSynchronize();
