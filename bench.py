@@ -41,7 +41,7 @@ ALG_BYTES_FORCE = 72.0     # force+integrate+collide sweep: R(16+16+4) + W(16+16
 ALG_BYTES_DENSITY = 20.0   # density+EOS sweep: R16 + W4
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 16.7M particles, from the committed
 # `ncu --set full` capture (profiles/r01_ncu_top_kernels_16m.csv)
-NCU_TRAFFIC_16M = {"density": 0.815e9 + 1.525e9, "force": 1.979e9 + 0.853e9}
+NCU_TRAFFIC_16M = {"density": 0.869e9 + 1.554e9, "force": 2.010e9 + 0.851e9}
 NU = 40.0
 
 
