@@ -175,6 +175,68 @@ DevParams sph_dev_params(const sphb200_ctx* ctx)
    return P;
 }
 
+// The step is a fixed sequence of 9-11 launches with fixed arguments (everything a kernel
+// needs lives in device memory or in the by-value DevParams), so it is captured once
+// into a CUDA graph and replayed: at the reference's default 32 768 particles the step
+// is launch bound (11 launches, ~0.28 ms) and the replay removes most of that.  The
+// graph is rebuilt after anything that changes an argument (set_params, upload_state,
+// set_stream).  Slab contexts (NCCL exchange per step) and timed steps (events between
+// the kernels) launch directly.
+void sph_graph_invalidate(sphb200_ctx* ctx)
+{
+   if (ctx->graph_exec)
+      cudaGraphExecDestroy(ctx->graph_exec);
+   ctx->graph_exec = nullptr;
+}
+
+static int step_once(sphb200_ctx* ctx)
+{
+   return ctx->params.neighbor_mode == SPHB200_NEIGHBORS_FULL ? sph_step_full(ctx) : sph_step_sampled(ctx);
+}
+
+static int step_graph(sphb200_ctx* ctx, int n_steps)
+{
+   cudaStream_t st = ctx->stream;
+   if (!ctx->graph_exec)
+   {
+      const long long l0 = ctx->launches;
+      SPH_CUDA_CHECK(ctx, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+      int rc = step_once(ctx);
+      cudaGraph_t g = nullptr;
+      cudaError_t e = cudaStreamEndCapture(st, &g);
+      if (rc || e != cudaSuccess)
+      {
+         if (g)
+            cudaGraphDestroy(g);
+         cudaGetLastError();
+         return rc ? rc : sph_fail(ctx, SPHB200_E_CUDA, std::string("step capture: ") + cudaGetErrorString(e));
+      }
+      e = cudaGraphInstantiate(&ctx->graph_exec, g, 0);
+      cudaGraphDestroy(g);
+      if (e != cudaSuccess)
+      {
+         ctx->graph_exec = nullptr;
+         return sph_fail(ctx, SPHB200_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+      }
+      ctx->graph_launches = ctx->launches - l0;
+      ctx->launches = l0;
+   }
+   for (int s = 0; s < n_steps; s++)
+   {
+      SPH_CUDA_CHECK(ctx, cudaGraphLaunch(ctx->graph_exec, st));
+      ctx->launches += ctx->graph_launches;
+   }
+   // host-side view of what a step leaves behind (the capture ran the same code once)
+   const bool full = ctx->params.neighbor_mode == SPHB200_NEIGHBORS_FULL;
+   ctx->lists_valid = !full;
+   ctx->snapshot_valid = full;
+   ctx->unsorted_valid = false;
+   ctx->voxel_ids_valid = true;
+   ctx->idx_order = ctx->idx_sorted;
+   ctx->stepped = true;
+   return SPHB200_OK;
+}
+
 extern "C" {
 
 int sphb200_default_params(SphParams* p)
@@ -246,6 +308,8 @@ int sphb200_create(const SphParams* p, int device, sphb200_ctx** out)
    ctx->capacity = p->particle_count;
    ctx->n_local = p->particle_count;
    ctx->n_owned = p->particle_count;
+   const char* no_graph = getenv("SPHB200_NO_GRAPH");
+   ctx->use_graph = !(no_graph && no_graph[0] == '1');
    ctx->cells_voxel = p->grid_x * p->grid_y * p->grid_z;
    ctx->cells_fine = 8 * ctx->cells_voxel;
    ctx->cells_alloc = p->neighbor_mode == SPHB200_NEIGHBORS_FULL ? ctx->cells_fine : ctx->cells_voxel;
@@ -313,6 +377,7 @@ int sphb200_destroy(sphb200_ctx* ctx)
    if (ctx->stream)
       cudaStreamSynchronize(ctx->stream);
    sph_comm_free(ctx);
+   sph_graph_invalidate(ctx);
    void* bufs[] = {ctx->pos4, ctx->vel4, ctx->gid, ctx->keys, ctx->keys_sorted, ctx->idx_iota, ctx->idx_sorted,
                    ctx->cell_count, ctx->cell_start, ctx->slot_state, ctx->idx_fixed, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
                    ctx->s_acc4, ctx->s_count, ctx->nbr_idx, ctx->nbr_dist, ctx->nbr_count, ctx->rho, ctx->acc4,
@@ -361,6 +426,7 @@ int sphb200_set_params(sphb200_ctx* ctx, const SphParams* p)
                       "set_params: particle_count/grid/examine_count/neighbor_mode/h/scale are fixed at create");
    ctx->params = *p;
    derive(ctx->params, ctx->derived);
+   sph_graph_invalidate(ctx);
    return SPHB200_OK;
 }
 
@@ -370,6 +436,7 @@ int sphb200_set_stream(sphb200_ctx* ctx, void* cuda_stream)
       return sph_fail(nullptr, SPHB200_E_INVALID, "null context");
    SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
    SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+   sph_graph_invalidate(ctx);
    if (ctx->own_stream)
       cudaStreamDestroy(ctx->stream);
    if (cuda_stream)
@@ -419,6 +486,7 @@ int sphb200_upload_state(sphb200_ctx* ctx, const float* pos_xyz, const float* ve
    else
       ctx->uniform_mass = true;
    ctx->n_local = ctx->n_owned = n;
+   sph_graph_invalidate(ctx);
    ctx->lists_valid = false;
    ctx->snapshot_valid = false;
    ctx->voxel_ids_valid = false;
@@ -432,6 +500,8 @@ int sphb200_step(sphb200_ctx* ctx, int n_steps)
    if (!ctx || n_steps < 0)
       return sph_fail(ctx, SPHB200_E_INVALID, "step: bad argument");
    SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   if (ctx->use_graph && !ctx->comm && !ctx->params.enable_timers && n_steps > 0 && ctx->n_local > 0)
+      return step_graph(ctx, n_steps);
    for (int s = 0; s < n_steps; s++)
    {
       int rc;

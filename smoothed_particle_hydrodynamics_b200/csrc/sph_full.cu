@@ -55,6 +55,13 @@ constexpr int kCapMass = (12 * (kCap + 4)) / 16 - 4;   // ... with per-particle 
 constexpr int WCAP = 32;                    // hit-mask records per particle (32 candidates each)
 constexpr unsigned kNoStream = 0xffu;       // info.nw value: no stream, scan instead
 constexpr int RSM = 16;                     // records per thread kept in shared memory by the force sweep
+#ifndef SPH_FORCE_ILP
+#define SPH_FORCE_ILP 2
+#endif
+#ifndef SPH_FORCE_CTAS
+#define SPH_FORCE_CTAS 4
+#endif
+constexpr int kForceIlp = SPH_FORCE_ILP;     // neighbours in flight per lane of the force sweep
 constexpr int kForceThreads = 128;
 constexpr int kFlatThreads = 128;
 
@@ -917,7 +924,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtas)
 // Particles without a stream (dense fallback tiles, record overflow, or the flat
 // density kernel) scan their 27 cells instead.
 template <bool UNIT_SCALE>
-__global__ void __launch_bounds__(kForceThreads, 4)
+__global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    k_force_stream(DevParams P, const float4* __restrict__ s_pos4, const float4* __restrict__ s_posA4,
                   const float4* __restrict__ s_velB4, const float* __restrict__ s_rho,
                   const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ cell_start,
@@ -986,25 +993,34 @@ __global__ void __launch_bounds__(kForceThreads, 4)
       m &= ~(0x80000000u >> lead);
       return base + lead;
    };
-   // two hits per trip: their gathers and arithmetic are independent (ILP); only the
+   // kForceIlp hits per trip: their gathers and arithmetic are independent (ILP); only the
    // accumulation is ordered (the in-loop viscosity scaling, sph.cpp:880-882)
    const int nmax = __reduce_max_sync(0xffffffffu, nhits);
 #pragma unroll 1
-   for (int it = 0; it < nmax; it += 2)
+   for (int it = 0; it < nmax; it += kForceIlp)
    {
-      int j0 = kk, j1 = kk;
-      if (it < nhits)
-         j0 = next_hit();
-      if (it + 1 < nhits)
-         j1 = next_hit();
-      float4 pj0 = __ldg(&s_posA4[j0]);
-      float4 vj0 = __ldg(&s_velB4[j0]);
-      float4 pj1 = __ldg(&s_posA4[j1]);
-      float4 vj1 = __ldg(&s_velB4[j1]);
-      PairTerm t0 = force_term<UNIT_SCALE>(P, I, pj0, vj0, j0 != kk);
-      PairTerm t1 = force_term<UNIT_SCALE>(P, I, pj1, vj1, j1 != kk);
-      force_accumulate(I, t0, pg, vt, count);
-      force_accumulate(I, t1, pg, vt, count);
+      int j[kForceIlp];
+      float4 pj[kForceIlp], vj[kForceIlp];
+#pragma unroll
+      for (int q = 0; q < kForceIlp; q++)
+      {
+         j[q] = kk;
+         if (it + q < nhits)
+            j[q] = next_hit();
+      }
+#pragma unroll
+      for (int q = 0; q < kForceIlp; q++)
+      {
+         pj[q] = __ldg(&s_posA4[j[q]]);
+         vj[q] = __ldg(&s_velB4[j[q]]);
+      }
+      PairTerm t[kForceIlp];
+#pragma unroll
+      for (int q = 0; q < kForceIlp; q++)
+         t[q] = force_term<UNIT_SCALE>(P, I, pj[q], vj[q], j[q] != kk);
+#pragma unroll
+      for (int q = 0; q < kForceIlp; q++)
+         force_accumulate(I, t[q], pg, vt, count);
    }
    if (scan && active)
    {

@@ -126,6 +126,10 @@ struct sphb200_ctx
    float* stage_f;             // N floats: mass staging for upload / download
    bool unsorted_valid;        // rho / acc4 / nbr_count hold the last FULL step, particle order
 
+   cudaGraphExec_t graph_exec; // one captured step (sph_capi.cu: step_graph), or null
+   long long graph_launches;   // kernels per replay
+   bool use_graph;             // env SPHB200_NO_GRAPH=1 turns the replay off (A/B)
+
    cudaEvent_t ev[8];
    float phase_ms[6];
    bool stepped;
@@ -142,6 +146,7 @@ struct sphb200_ctx
    } while (0)
 
 int sph_fail(sphb200_ctx* ctx, int code, const std::string& msg);
+void sph_graph_invalidate(sphb200_ctx* ctx);
 DevParams sph_dev_params(const sphb200_ctx* ctx);
 
 // sph_grid.cu
