@@ -35,17 +35,6 @@
 
 #include "sph_math.cuh"
 
-struct SlabMsgHeader
-{
-   unsigned n_migrants, n_ghosts, pad0, pad1;
-};
-
-struct SlabEntry      // 32 bytes per particle on the wire
-{
-   float4 pos;        // x, y, z, mass
-   float4 vel;        // vx, vy, vz, global id (bits)
-};
-
 struct SlabComm
 {
    ncclComm_t nccl;
@@ -60,6 +49,7 @@ struct SlabComm
    uint32_t* free_list;      // FREE slot indices of this step
    unsigned* counters;       // [0] n_free, [1] overflow flag
    unsigned h_counters[2];
+   bool msgs_ready;          // the last force sweep already built the outgoing messages
 };
 
 namespace
@@ -120,89 +110,58 @@ NcclApi& nccl_api()
 
 constexpr int kThreads = 256;
 
-__device__ __forceinline__ SlabEntry* msg_entries(unsigned char* msg)
+// First exchange after an upload: classify every slot, build the outgoing messages and
+// the free list.  (Later exchanges get their messages from the force sweep, which has
+// every particle's new position at hand -- sph_slab_emit in sph_math.cuh -- and only
+// need k_slab_freelist.)
+__global__ void __launch_bounds__(kThreads)
+   k_slab_pack(DevParams P, int capacity, const float4* __restrict__ pos4, const float4* __restrict__ vel4,
+               const uint32_t* __restrict__ gid, unsigned char* __restrict__ state,
+               uint32_t* __restrict__ free_list, unsigned* __restrict__ counters)
 {
-   return reinterpret_cast<SlabEntry*>(msg + sizeof(SlabMsgHeader));
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   const bool valid = i < capacity;
+   unsigned char st = valid ? state[i] : (unsigned char)SLOT_OWNED;
+   const bool owned = valid && st == SLOT_OWNED;
+   float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p;
+   if (owned)
+   {
+      p = pos4[i];
+      v = vel4[i];
+      v.w = __uint_as_float(gid[i]);
+   }
+   const unsigned char ns = sph_slab_emit(P, owned, p, v);
+   if (owned)
+      st = ns == SLOT_LEAVING_GHOST ? (unsigned char)SLOT_GHOST : ns == SLOT_LEAVING_FREE ? (unsigned char)SLOT_FREE : st;
+   else if (valid)
+      st = SLOT_FREE;      // FREE stays free; last step's ghosts are dropped (fresh ones arrive with the unpack)
+   const bool is_free = valid && st == SLOT_FREE;
+   const unsigned f = sph_warp_append(&counters[0], is_free);
+   if (is_free)
+      free_list[f] = (uint32_t)i;
+   if (valid)
+      state[i] = st;
 }
 
-// classify every slot, build this step's outgoing messages and the free list
+// Exchanges whose messages were built by the force sweep: one pass over the slot states
+// drops last step's ghosts, retires the migrants and lists the free slots.
 __global__ void __launch_bounds__(kThreads)
-   k_slab_pack(DevParams P, int capacity, int z0, int z1, int has_down, int has_up, int mig_cap, int ghost_cap,
-               const float4* __restrict__ pos4, const float4* __restrict__ vel4, const uint32_t* __restrict__ gid,
-               unsigned char* __restrict__ state, unsigned char* __restrict__ msg_down,
-               unsigned char* __restrict__ msg_up, uint32_t* __restrict__ free_list, unsigned* __restrict__ counters)
+   k_slab_freelist(int capacity, unsigned char* __restrict__ state, uint32_t* __restrict__ free_list,
+                   unsigned* __restrict__ counters)
 {
-   int i = blockIdx.x * blockDim.x + threadIdx.x;
-   if (i >= capacity)
-      return;
-   unsigned char st = state[i];
-   if (st != SLOT_OWNED)
-   {
-      // FREE stays free; last step's ghosts are dropped (fresh ones arrive below)
-      state[i] = SLOT_FREE;
-      free_list[atomicAdd(&counters[0], 1u)] = (uint32_t)i;
-      return;
-   }
-   float4 p = pos4[i];
-   int vz = sph_voxel_coord(p.z, P.h_times2_inv, P.gz_global);
-   int dir = -1;          // message this particle goes into: 0 down, 1 up
-   bool migrant = false;
-   if (vz >= z1 && has_up)
-   {
-      dir = 1;
-      migrant = true;
-   }
-   else if (vz < z0 && has_down)
-   {
-      dir = 0;
-      migrant = true;
-   }
-   else if (vz == z1 - 1 && has_up)
-      dir = 1;
-   bool also_down = !migrant && vz == z0 && has_down;   // 1-layer slabs ghost both ways
-   if (dir < 0 && !also_down)
-      return;
-   float4 v = vel4[i];
-   SlabEntry e;
-   e.pos = p;
-   e.vel = make_float4(v.x, v.y, v.z, __uint_as_float(gid[i]));
-   if (migrant)
-   {
-      unsigned char* msg = dir ? msg_up : msg_down;
-      SlabMsgHeader* hdr = reinterpret_cast<SlabMsgHeader*>(msg);
-      unsigned slot = atomicAdd(&hdr->n_migrants, 1u);
-      if (slot < (unsigned)mig_cap)
-         msg_entries(msg)[slot] = e;
-      else
-         atomicMax(&counters[1], 1u);
-      bool keep_ghost = dir ? (vz == z1) : (vz == z0 - 1);
-      if (keep_ghost)
-         state[i] = SLOT_GHOST;
-      else
-      {
-         state[i] = SLOT_FREE;
-         free_list[atomicAdd(&counters[0], 1u)] = (uint32_t)i;
-      }
-      return;
-   }
-   if (dir == 1)
-   {
-      SlabMsgHeader* hdr = reinterpret_cast<SlabMsgHeader*>(msg_up);
-      unsigned slot = atomicAdd(&hdr->n_ghosts, 1u);
-      if (slot < (unsigned)ghost_cap)
-         msg_entries(msg_up)[mig_cap + slot] = e;
-      else
-         atomicMax(&counters[1], 1u);
-   }
-   if (also_down)
-   {
-      SlabMsgHeader* hdr = reinterpret_cast<SlabMsgHeader*>(msg_down);
-      unsigned slot = atomicAdd(&hdr->n_ghosts, 1u);
-      if (slot < (unsigned)ghost_cap)
-         msg_entries(msg_down)[mig_cap + slot] = e;
-      else
-         atomicMax(&counters[1], 1u);
-   }
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   const bool valid = i < capacity;
+   unsigned char st = valid ? state[i] : (unsigned char)SLOT_OWNED;
+   if (st == SLOT_LEAVING_GHOST)
+      st = SLOT_GHOST;
+   else if (st != SLOT_OWNED)
+      st = SLOT_FREE;
+   const bool is_free = valid && st == SLOT_FREE;
+   const unsigned f = sph_warp_append(&counters[0], is_free);
+   if (is_free)
+      free_list[f] = (uint32_t)i;
+   if (valid)
+      state[i] = st;
 }
 
 // arrivals of both incoming messages into free slots
@@ -229,22 +188,22 @@ __global__ void __launch_bounds__(kThreads)
    unsigned char st;
    if (a < c0)
    {
-      src = msg_entries(const_cast<unsigned char*>(msg_down)) + a;
+      src = sph_msg_entries(const_cast<unsigned char*>(msg_down)) + a;
       st = SLOT_OWNED;
    }
    else if (a < c0 + c1)
    {
-      src = msg_entries(const_cast<unsigned char*>(msg_down)) + mig_cap + (a - c0);
+      src = sph_msg_entries(const_cast<unsigned char*>(msg_down)) + mig_cap + (a - c0);
       st = SLOT_GHOST;
    }
    else if (a < c0 + c1 + c2)
    {
-      src = msg_entries(const_cast<unsigned char*>(msg_up)) + (a - c0 - c1);
+      src = sph_msg_entries(const_cast<unsigned char*>(msg_up)) + (a - c0 - c1);
       st = SLOT_OWNED;
    }
    else
    {
-      src = msg_entries(const_cast<unsigned char*>(msg_up)) + mig_cap + (a - c0 - c1 - c2);
+      src = sph_msg_entries(const_cast<unsigned char*>(msg_up)) + mig_cap + (a - c0 - c1 - c2);
       st = SLOT_GHOST;
    }
    SlabEntry e = *src;
@@ -341,6 +300,30 @@ void sph_comm_dev_params(const sphb200_ctx* ctx, DevParams& P)
    P.slot_state = ctx->slot_state;
    P.slot_gid = ctx->gid;
    P.d_nlive = ctx->cell_start + ctx->cells_fine;
+   P.own_z0 = c->z0;
+   P.own_z1 = c->z1;
+   P.has_down = c->rank > 0;
+   P.has_up = c->rank < c->nranks - 1;
+   P.mig_cap = c->mig_cap;
+   P.ghost_cap = c->ghost_cap;
+   P.msg_down = c->send[0];
+   P.msg_up = c->send[1];
+   P.comm_counters = c->counters;
+}
+
+// start of a slab's local step: the previous exchange has consumed the outgoing
+// messages; empty them for the force sweep of this step
+int sph_comm_begin_step(sphb200_ctx* ctx)
+{
+   SlabComm* c = ctx->comm;
+   for (int d = 0; d < 2; d++)
+      SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->send[d], 0, sizeof(SlabMsgHeader), ctx->stream));
+   return SPHB200_OK;
+}
+
+void sph_comm_end_step(sphb200_ctx* ctx)
+{
+   ctx->comm->msgs_ready = true;
 }
 
 void sph_comm_free(sphb200_ctx* ctx)
@@ -373,17 +356,23 @@ static int slab_pack(sphb200_ctx* ctx)
    SlabComm* c = ctx->comm;
    DevParams P = sph_dev_params(ctx);
    cudaStream_t st = ctx->stream;
-   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->counters, 0, sizeof(unsigned) * 2, st));
-   for (int d = 0; d < 2; d++)
-      SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->send[d], 0, sizeof(SlabMsgHeader), st));
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->counters, 0, sizeof(unsigned), st));   // [1], the overflow flag, is sticky
    if (ctx->capacity > 0)
    {
-      k_slab_pack<<<blocks_for(ctx->capacity), kThreads, 0, st>>>(
-         P, ctx->capacity, c->z0, c->z1, c->rank > 0, c->rank < c->nranks - 1, c->mig_cap, c->ghost_cap, ctx->pos4,
-         ctx->vel4, ctx->gid, ctx->slot_state, c->send[0], c->send[1], c->free_list, c->counters);
+      if (c->msgs_ready)
+         k_slab_freelist<<<blocks_for(ctx->capacity), kThreads, 0, st>>>(ctx->capacity, ctx->slot_state, c->free_list,
+                                                                         c->counters);
+      else
+      {
+         for (int d = 0; d < 2; d++)
+            SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->send[d], 0, sizeof(SlabMsgHeader), st));
+         k_slab_pack<<<blocks_for(ctx->capacity), kThreads, 0, st>>>(P, ctx->capacity, ctx->pos4, ctx->vel4, ctx->gid,
+                                                                     ctx->slot_state, c->free_list, c->counters);
+      }
       ctx->launches++;
       SPH_CUDA_CHECK(ctx, cudaGetLastError());
    }
+   c->msgs_ready = false;
    return SPHB200_OK;
 }
 
@@ -548,7 +537,7 @@ int sphb200_get_local_count(const sphb200_ctx* ctx, int* owned, int* ghosts)
    int no = 0, ng = 0;
    for (unsigned char s : st)
    {
-      no += s == SLOT_OWNED;
+      no += s == SLOT_OWNED || s == SLOT_LEAVING_FREE || s == SLOT_LEAVING_GHOST;
       ng += s == SLOT_GHOST;
    }
    if (owned) *owned = no;
@@ -592,6 +581,8 @@ int sphb200_upload_slab(sphb200_ctx* ctx, int count, const float* pos_xyz, const
       for (int i = 0; i < count && ctx->uniform_mass; i++)
          ctx->uniform_mass = mass[i] == 1.0f;
    ctx->n_owned = count;
+   ctx->comm->msgs_ready = false;
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->comm->counters, 0, sizeof(unsigned) * 2, st));
    ctx->lists_valid = false;
    ctx->snapshot_valid = false;
    ctx->voxel_ids_valid = false;
@@ -632,7 +623,7 @@ int sphb200_download_slab(sphb200_ctx* ctx, int field, void* dst, size_t dst_byt
    SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
    size_t n = 0;
    for (size_t i = 0; i < cap; i++)
-      if (st[i] == SLOT_OWNED)
+      if (st[i] == SLOT_OWNED || st[i] == SLOT_LEAVING_FREE || st[i] == SLOT_LEAVING_GHOST)
       {
          if ((n + 1) * per > dst_bytes)
             return sph_fail(ctx, SPHB200_E_INVALID, "download_slab: destination too small");

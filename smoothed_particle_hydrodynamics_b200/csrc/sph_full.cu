@@ -280,7 +280,8 @@ __device__ __forceinline__ void force_store(const DevParams& P, int k, const For
                                             const float4* __restrict__ s_pos4,
                                             const uint32_t* __restrict__ idx_sorted, float4* __restrict__ pos4,
                                             float4* __restrict__ vel4, float4* __restrict__ s_acc4,
-                                            int* __restrict__ s_count, double& ek, double& ep)
+                                            int* __restrict__ s_count, double& ek, double& ep, float4& new_pos,
+                                            float4& new_vel)
 {
    Vec3 a = sph_finish_acceleration(P, vt, pg, I.x, I.y, I.z);
    float mass = s_pos4[k].w;
@@ -289,8 +290,10 @@ __device__ __forceinline__ void force_store(const DevParams& P, int k, const For
    float e_kin, e_pot;
    sph_integrate(P, r, v, a, mass, e_kin, e_pot);
    uint32_t o = idx_sorted[k];
-   pos4[o] = make_float4(r[0], r[1], r[2], mass);
-   vel4[o] = make_float4(v[0], v[1], v[2], 0.0f);
+   new_pos = make_float4(r[0], r[1], r[2], mass);
+   new_vel = make_float4(v[0], v[1], v[2], 0.0f);
+   pos4[o] = new_pos;
+   vel4[o] = new_vel;
    s_acc4[k] = make_float4(a.x, a.y, a.z, 0.0f);
    s_count[k] = count;
    ek = e_kin;
@@ -1031,12 +1034,38 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
          for (int j = b[r]; j < e[r]; j++)
             count += force_candidate<UNIT_SCALE>(P, I, __ldg(&s_posA4[j]), __ldg(&s_velB4[j]), j != k, pg, vt);
    }
+   float4 new_pos = make_float4(0.0f, 0.0f, 0.0f, 0.0f), new_vel = new_pos;
    if (active)
    {
-      force_store(P, k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, ek, ep);
+      force_store(P, k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, ek, ep, new_pos, new_vel);
       cnt = (unsigned long long)count;
       cmax = count;
       cmin = count;
+   }
+   if (P.slab)
+   {
+      // Multi-GPU: the new position decides, right here, whether the particle goes into
+      // the next halo message (boundary layer) or migrates; the messages are complete
+      // when this kernel ends and the next exchange needs no pass over the particles.
+      bool owned = active;
+      uint32_t o = 0;
+      if (k < sph_live_count(P))
+      {
+         o = idx_sorted[k];
+         if (!active && P.slot_state[o] == SLOT_OWNED)
+         {
+            // an owned particle parked in a ghost layer (it crossed more than one slab in a
+            // step): not integrated here, forwarded one rank per step
+            new_pos = pos4[o];
+            new_vel = vel4[o];
+            owned = true;
+         }
+      }
+      if (owned)
+         new_vel.w = __uint_as_float(P.slot_gid[o]);
+      const unsigned char st = sph_slab_emit(P, owned, new_pos, new_vel);
+      if (owned && st != SLOT_OWNED)
+         P.slot_state[o] = st;
    }
    sph_block_reduce_scalars(ek, ep, cnt, cmax, cmin, block_partials, scal);
 }
@@ -1130,7 +1159,10 @@ int sph_step_full(sphb200_ctx* ctx)
    cudaStream_t st = ctx->stream;
    const bool timed = ctx->params.enable_timers != 0;
    if (timed) cudaEventRecord(ctx->ev[0], st);
-   int rc = sph_bin_and_sort(ctx, true);
+   int rc = ctx->comm ? sph_comm_begin_step(ctx) : SPHB200_OK;
+   if (rc)
+      return rc;
+   rc = sph_bin_and_sort(ctx, true);
    if (rc)
       return rc;
    if (timed) cudaEventRecord(ctx->ev[1], st);
@@ -1175,6 +1207,8 @@ int sph_step_full(sphb200_ctx* ctx)
    if (rc)
       return rc;
    if (timed) cudaEventRecord(ctx->ev[6], st);
+   if (ctx->comm)
+      sph_comm_end_step(ctx);
    ctx->lists_valid = false;
    ctx->snapshot_valid = true;
    ctx->unsorted_valid = false;

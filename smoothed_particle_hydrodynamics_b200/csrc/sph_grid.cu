@@ -38,14 +38,20 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(DevParams P, int cells, 
                                                          int* __restrict__ voxel_id_out)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (P.slab)
+   {
+      // FREE slots all fall into the sentinel cell: one atomic per warp, not per slot
+      const bool is_free = i < P.n && P.slot_state[i] == SLOT_FREE;
+      const unsigned f = sph_warp_append(&cell_count[cells], is_free);
+      if (is_free)
+      {
+         keys[i] = (uint32_t)cells;
+         cell_slot[i] = f;
+         return;
+      }
+   }
    if (i >= P.n)
       return;
-   if (P.slab && P.slot_state[i] == SLOT_FREE)
-   {
-      keys[i] = (uint32_t)cells;
-      cell_slot[i] = atomicAdd(&cell_count[cells], 1u);
-      return;
-   }
    float4 p = pos4[i];
    int vx = sph_voxel_coord(p.x, P.h_times2_inv, P.gx);
    int vy = sph_voxel_coord(p.y, P.h_times2_inv, P.gy);

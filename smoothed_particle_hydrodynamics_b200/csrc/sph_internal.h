@@ -38,12 +38,33 @@ struct DevParams
    int gz_global;         // voxel layers of the whole box (binning clamps against this, like the reference)
    int vz_offset;         // first voxel layer of the local grid (global layer index)
    int ghost_lo, ghost_hi;// ghost voxel layers present below / above the owned range (0 or 1)
-   const unsigned char* slot_state;   // per slot: SLOT_FREE / SLOT_OWNED / SLOT_GHOST
+   unsigned char* slot_state;         // per slot: SLOT_*
    const uint32_t* slot_gid;          // per slot: global particle id
    const uint32_t* d_nlive;           // live (non-FREE) particles = cell_start[cells]
+   // halo messages of the NEXT exchange, appended to by the force sweep (sph_comm.cu)
+   int own_z0, own_z1;                // owned voxel layers (global layer indices)
+   int has_down, has_up;              // neighbour ranks present
+   int mig_cap, ghost_cap;            // message capacities (entries)
+   unsigned char* msg_down;           // to rank - 1
+   unsigned char* msg_up;             // to rank + 1
+   unsigned* comm_counters;           // [0] free slots of this exchange, [1] overflow flag
 };
 
-enum { SLOT_FREE = 0, SLOT_OWNED = 1, SLOT_GHOST = 2 };
+// SLOT_LEAVING_*: an OWNED particle the force sweep has already put into a migrant
+// message; it still counts as owned until the next exchange turns the slot into a
+// FREE slot / a GHOST (it sits in the neighbour's boundary layer, needed here as ghost).
+enum { SLOT_FREE = 0, SLOT_OWNED = 1, SLOT_GHOST = 2, SLOT_LEAVING_FREE = 3, SLOT_LEAVING_GHOST = 4 };
+
+struct SlabMsgHeader
+{
+   unsigned n_migrants, n_ghosts, pad0, pad1;
+};
+
+struct SlabEntry      // 32 bytes per particle on the wire
+{
+   float4 pos;        // x, y, z, mass
+   float4 vel;        // vx, vy, vz, global id (bits)
+};
 
 // number of particles a kernel has to process: by value on a single GPU, read from
 // the cell table (no host round trip) in slab mode
@@ -165,6 +186,8 @@ int sph_reset_scalars(sphb200_ctx* ctx);
 int sph_finish_scalars(sphb200_ctx* ctx, int blocks);
 // sph_comm.cu
 int sph_comm_exchange(sphb200_ctx* ctx);
+int sph_comm_begin_step(sphb200_ctx* ctx);
+void sph_comm_end_step(sphb200_ctx* ctx);
 void sph_comm_free(sphb200_ctx* ctx);
 void sph_comm_dev_params(const sphb200_ctx* ctx, DevParams& P);
 int sph_grid_alloc(sphb200_ctx* ctx);

@@ -205,6 +205,72 @@ __device__ __forceinline__ void sph_integrate(const DevParams& P, float r[3], fl
    }
 }
 
+// ---- slab halo messages (multi-GPU, sph_comm.cu) --------------------------------
+__device__ __forceinline__ SlabEntry* sph_msg_entries(unsigned char* msg)
+{
+   return reinterpret_cast<SlabEntry*>(msg + sizeof(SlabMsgHeader));
+}
+
+// slot in a message section for every lane with `want`, one atomic per warp.  Must be
+// called by all 32 lanes of a converged warp.
+__device__ __forceinline__ unsigned sph_warp_append(unsigned* counter, bool want)
+{
+   const unsigned m = __ballot_sync(0xffffffffu, want);
+   if (m == 0u)
+      return 0u;
+   const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+   unsigned base = 0;
+   if (lane == leader)
+      base = atomicAdd(counter, (unsigned)__popc(m));
+   base = __shfl_sync(0xffffffffu, base, leader);
+   return base + (unsigned)__popc(m & ((1u << lane) - 1u));
+}
+
+// Exchange rules for an OWNED particle at position z (sph_comm.cu header): appends it to
+// the outgoing messages as a migrant or as a boundary-layer ghost and returns the state
+// its slot takes.  All 32 lanes of the warp call this; `owned` selects the real ones.
+__device__ __forceinline__ unsigned char sph_slab_emit(const DevParams& P, bool owned, float4 pos, float4 vel_gid)
+{
+   const int vz = sph_voxel_coord(pos.z, P.h_times2_inv, P.gz_global);
+   const bool mig_up = owned && vz >= P.own_z1 && P.has_up;
+   const bool mig_down = owned && !mig_up && vz < P.own_z0 && P.has_down;
+   const bool migrant = mig_up || mig_down;
+   const bool ghost_up = owned && !migrant && vz == P.own_z1 - 1 && P.has_up;
+   const bool ghost_down = owned && !migrant && vz == P.own_z0 && P.has_down;   // 1-layer slabs ghost both ways
+   SlabMsgHeader* hu = reinterpret_cast<SlabMsgHeader*>(P.msg_up);
+   SlabMsgHeader* hd = reinterpret_cast<SlabMsgHeader*>(P.msg_down);
+   SlabEntry e;
+   e.pos = pos;
+   e.vel = vel_gid;
+   bool overflow = false;
+   unsigned s = sph_warp_append(&hu->n_migrants, mig_up);
+   if (mig_up)
+   {
+      if (s < (unsigned)P.mig_cap) sph_msg_entries(P.msg_up)[s] = e; else overflow = true;
+   }
+   s = sph_warp_append(&hd->n_migrants, mig_down);
+   if (mig_down)
+   {
+      if (s < (unsigned)P.mig_cap) sph_msg_entries(P.msg_down)[s] = e; else overflow = true;
+   }
+   s = sph_warp_append(&hu->n_ghosts, ghost_up);
+   if (ghost_up)
+   {
+      if (s < (unsigned)P.ghost_cap) sph_msg_entries(P.msg_up)[P.mig_cap + s] = e; else overflow = true;
+   }
+   s = sph_warp_append(&hd->n_ghosts, ghost_down);
+   if (ghost_down)
+   {
+      if (s < (unsigned)P.ghost_cap) sph_msg_entries(P.msg_down)[P.mig_cap + s] = e; else overflow = true;
+   }
+   if (overflow)
+      atomicMax(&P.comm_counters[1], 1u);
+   if (!migrant)
+      return SLOT_OWNED;
+   const bool keep_ghost = mig_up ? (vz == P.own_z1) : (vz == P.own_z0 - 1);
+   return keep_ghost ? SLOT_LEAVING_GHOST : SLOT_LEAVING_FREE;
+}
+
 // block-wide sum of (e_kin, e_pot) in double + neighbour statistics, one
 // partial per block (deterministic two-stage reduction; finished by
 // sph_finish_scalars).  blockDim.x must be a multiple of 32, <= 1024.
