@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(kThreads)
    else if (valid)
       st = SLOT_FREE;      // FREE stays free; last step's ghosts are dropped (fresh ones arrive with the unpack)
    const bool is_free = valid && st == SLOT_FREE;
-   const unsigned f = sph_warp_append(&counters[0], is_free);
+   const unsigned f = sph_block_append(&counters[0], is_free);
    if (is_free)
       free_list[f] = (uint32_t)i;
    if (valid)
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(kThreads)
    else if (st != SLOT_OWNED)
       st = SLOT_FREE;
    const bool is_free = valid && st == SLOT_FREE;
-   const unsigned f = sph_warp_append(&counters[0], is_free);
+   const unsigned f = sph_block_append(&counters[0], is_free);
    if (is_free)
       free_list[f] = (uint32_t)i;
    if (valid)

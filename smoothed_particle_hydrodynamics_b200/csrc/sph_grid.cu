@@ -40,9 +40,9 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(DevParams P, int cells, 
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (P.slab)
    {
-      // FREE slots all fall into the sentinel cell: one atomic per warp, not per slot
+      // FREE slots all fall into the sentinel cell: one atomic per block, not per slot
       const bool is_free = i < P.n && P.slot_state[i] == SLOT_FREE;
-      const unsigned f = sph_warp_append(&cell_count[cells], is_free);
+      const unsigned f = sph_block_append(&cell_count[cells], is_free);
       if (is_free)
       {
          keys[i] = (uint32_t)cells;

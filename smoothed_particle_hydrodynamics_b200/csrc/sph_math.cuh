@@ -226,6 +226,27 @@ __device__ __forceinline__ unsigned sph_warp_append(unsigned* counter, bool want
    return base + (unsigned)__popc(m & ((1u << lane) - 1u));
 }
 
+// the same for a whole CTA: one global atomic per block (free slots come by the million
+// and all append to one counter).  Must be called by every thread of the block.
+__device__ __forceinline__ unsigned sph_block_append(unsigned* counter, bool want)
+{
+   __shared__ unsigned s_total, s_base;
+   if (threadIdx.x == 0)
+      s_total = 0;
+   __syncthreads();
+   const unsigned m = __ballot_sync(0xffffffffu, want);
+   const int lane = threadIdx.x & 31;
+   unsigned warp_off = 0;
+   if (lane == 0 && m != 0u)
+      warp_off = atomicAdd(&s_total, (unsigned)__popc(m));
+   warp_off = __shfl_sync(0xffffffffu, warp_off, 0);
+   __syncthreads();
+   if (threadIdx.x == 0 && s_total != 0u)
+      s_base = atomicAdd(counter, s_total);
+   __syncthreads();
+   return s_base + warp_off + (unsigned)__popc(m & ((1u << lane) - 1u));
+}
+
 // Exchange rules for an OWNED particle at position z (sph_comm.cu header): appends it to
 // the outgoing messages as a migrant or as a boundary-layer ghost and returns the state
 // its slot takes.  All 32 lanes of the warp call this; `owned` selects the real ones.
