@@ -35,6 +35,30 @@ __global__ void __launch_bounds__(kThreads) k_pack_state(int n, const float* __r
    vel4[i] = make_float4(vel_xyz[3 * (size_t)i], vel_xyz[3 * (size_t)i + 1], vel_xyz[3 * (size_t)i + 2], 0.0f);
 }
 
+// the two halves of k_pack_state for sphb200_step_host (positions + masses first,
+// velocities while the step is already running)
+__global__ void __launch_bounds__(kThreads) k_pack_pos(int n, const float* __restrict__ pos_xyz,
+                                                        const float* __restrict__ mass, float4* __restrict__ pos4,
+                                                        int* __restrict__ mass_differs)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n)
+      return;
+   float m = mass ? mass[i] : 1.0f;
+   if (mass && m != mass[0])
+      *mass_differs = 1;
+   pos4[i] = make_float4(pos_xyz[3 * (size_t)i], pos_xyz[3 * (size_t)i + 1], pos_xyz[3 * (size_t)i + 2], m);
+}
+
+__global__ void __launch_bounds__(kThreads) k_pack_vel(int n, const float* __restrict__ vel_xyz,
+                                                        float4* __restrict__ vel4)
+{
+   int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= n)
+      return;
+   vel4[i] = make_float4(vel_xyz[3 * (size_t)i], vel_xyz[3 * (size_t)i + 1], vel_xyz[3 * (size_t)i + 2], 0.0f);
+}
+
 // float4 -> xyz-interleaved (Particle::mPosition layout, particle.h:15)
 __global__ void __launch_bounds__(kThreads) k_unpack_xyz(int n, const float4* __restrict__ src,
                                                           float* __restrict__ dst_xyz)
@@ -170,6 +194,7 @@ DevParams sph_dev_params(const sphb200_ctx* ctx)
    P.softening = d.softening;
    P.gvx = p.gravity[0]; P.gvy = p.gravity[1]; P.gvz = p.gravity[2];
    P.max_x = d.max_x; P.max_y = d.max_y; P.max_z = d.max_z;
+   P.defer_velocity = ctx->deferred_vel_event != nullptr;
    if (ctx->comm)
       sph_comm_dev_params(ctx, P);
    return P;
@@ -378,6 +403,12 @@ int sphb200_destroy(sphb200_ctx* ctx)
       cudaStreamSynchronize(ctx->stream);
    sph_comm_free(ctx);
    sph_graph_invalidate(ctx);
+   if (ctx->upload_stream)
+   {
+      cudaStreamDestroy(ctx->upload_stream);
+      cudaEventDestroy(ctx->upload_ev[0]);
+      cudaEventDestroy(ctx->upload_ev[1]);
+   }
    void* bufs[] = {ctx->pos4, ctx->vel4, ctx->gid, ctx->keys, ctx->keys_sorted, ctx->idx_iota, ctx->idx_sorted,
                    ctx->cell_count, ctx->cell_start, ctx->slot_state, ctx->idx_fixed, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
                    ctx->s_acc4, ctx->s_count, ctx->nbr_idx, ctx->nbr_dist, ctx->nbr_count, ctx->rho, ctx->acc4,
@@ -646,12 +677,69 @@ int sphb200_download(sphb200_ctx* ctx, int field, void* dst, size_t dst_bytes)
    return SPHB200_OK;
 }
 
+// Upload for sphb200_step_host in FULL mode: binning and the density sweep only need the
+// positions (and masses), so those go first and the step starts on them while the
+// velocities are still crossing PCIe on a second stream; the step joins that stream
+// before the force sweep (sph_step_full: deferred_vel_event, k_gather_vel).
+static int step_host_overlapped(sphb200_ctx* ctx, const float* pos_xyz, const float* vel_xyz, const float* mass)
+{
+   const int n = ctx->capacity;
+   cudaStream_t st = ctx->stream;
+   if (!ctx->upload_stream)
+   {
+      SPH_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; i++)
+         SPH_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&ctx->upload_ev[i], cudaEventDisableTiming));
+   }
+   cudaStream_t su = ctx->upload_stream;
+   float* d_pos = reinterpret_cast<float*>(ctx->s_posA4);   // staging; free until the density sweep writes them
+   float* d_vel = reinterpret_cast<float*>(ctx->s_acc4);    // staging; free until the force sweep writes it
+   int* d_flag = &ctx->d_scalars->overflow;
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(d_pos, pos_xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, st));
+   if (mass)
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->stage_f, mass, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, st));
+   SPH_CUDA_CHECK(ctx, cudaEventRecord(ctx->upload_ev[0], st));
+   // the velocity copy follows the position copy on the link instead of sharing it
+   SPH_CUDA_CHECK(ctx, cudaStreamWaitEvent(su, ctx->upload_ev[0], 0));
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(d_vel, vel_xyz, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, su));
+   k_pack_vel<<<blocks_for(n), kThreads, 0, su>>>(n, d_vel, ctx->vel4);
+   SPH_CUDA_CHECK(ctx, cudaEventRecord(ctx->upload_ev[1], su));
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+   k_pack_pos<<<blocks_for(n), kThreads, 0, st>>>(n, d_pos, mass ? ctx->stage_f : nullptr, ctx->pos4, d_flag);
+   ctx->launches += 2;
+   SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   int differs = 0;
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(&differs, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+   ctx->uniform_mass = differs == 0;
+   ctx->n_local = ctx->n_owned = n;
+   sph_graph_invalidate(ctx);
+   ctx->voxel_ids_valid = false;
+   ctx->deferred_vel_event = ctx->upload_ev[1];
+   int rc = sph_step_full(ctx);
+   ctx->deferred_vel_event = nullptr;
+   ctx->stepped = rc == SPHB200_OK;
+   return rc;
+}
+
 int sphb200_step_host(sphb200_ctx* ctx, float* pos_xyz, float* vel_xyz, const float* mass)
 {
-   int rc = sphb200_upload_state(ctx, pos_xyz, vel_xyz, mass);
-   if (rc)
-      return rc;
-   rc = sphb200_step(ctx, 1);
+   if (!ctx || !pos_xyz || !vel_xyz)
+      return sph_fail(ctx, SPHB200_E_INVALID, "step_host: null argument");
+   int rc;
+   if (!ctx->comm && ctx->params.neighbor_mode == SPHB200_NEIGHBORS_FULL && !ctx->params.enable_timers &&
+       ctx->params.kernel_variant != 1 && ctx->capacity > 0)
+   {
+      SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+      rc = step_host_overlapped(ctx, pos_xyz, vel_xyz, mass);
+   }
+   else
+   {
+      rc = sphb200_upload_state(ctx, pos_xyz, vel_xyz, mass);
+      if (rc)
+         return rc;
+      rc = sphb200_step(ctx, 1);
+   }
    if (rc)
       return rc;
    const int n = ctx->n_local;

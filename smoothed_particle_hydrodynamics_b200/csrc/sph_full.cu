@@ -269,7 +269,8 @@ __device__ __forceinline__ void density_store(const DevParams& P, int k, float4 
 {
    float fA, fB;
    sph_force_coeffs(P, rho, pi.w, fA, fB);
-   float4 v = __ldg(&vel4[idx_sorted[k]]);
+   // step_host uploads the velocities while this sweep runs: then k_gather_vel fills them in
+   float4 v = P.defer_velocity ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : __ldg(&vel4[idx_sorted[k]]);
    s_rho[k] = rho;
    s_posA4[k] = make_float4(pi.x, pi.y, pi.z, fA);
    s_velB4[k] = make_float4(v.x, v.y, v.z, fB);
@@ -1070,6 +1071,18 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    sph_block_reduce_scalars(ek, ep, cnt, cmax, cmin, block_partials, scal);
 }
 
+// velocities into the force records after a density sweep that ran with defer_velocity
+__global__ void __launch_bounds__(kFlatThreads)
+   k_gather_vel(DevParams P, const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ vel4,
+                float4* __restrict__ s_velB4)
+{
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k >= sph_live_count(P))
+      return;
+   float4 v = __ldg(&vel4[idx_sorted[k]]);
+   s_velB4[k] = make_float4(v.x, v.y, v.z, s_velB4[k].w);
+}
+
 // ---- on-demand outputs --------------------------------------------------------
 
 // mNeighbors / mNeighborDistancesScaled of the last step (sph.h:173-174) in the
@@ -1188,6 +1201,15 @@ int sph_step_full(sphb200_ctx* ctx)
          P, ctx->s_pos4, ctx->keys_sorted, ctx->cell_start, ctx->idx_order, ctx->vel4, ctx->s_posA4, ctx->s_velB4,
          ctx->s_rho, ctx->hit_info);
    if (timed) cudaEventRecord(ctx->ev[3], st);
+   if (ctx->deferred_vel_event)
+   {
+      // sphb200_step_host: the velocity upload ran on a second stream beside binning and the
+      // density sweep; join it here
+      SPH_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->deferred_vel_event, 0));
+      k_gather_vel<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, st>>>(P, ctx->idx_order, ctx->vel4,
+                                                                                  ctx->s_velB4);
+      ctx->launches++;
+   }
    if (timed) cudaEventRecord(ctx->ev[4], st);
    const int blocks = (n + kForceThreads - 1) / kForceThreads;
    if (P.scale == 1.0f)

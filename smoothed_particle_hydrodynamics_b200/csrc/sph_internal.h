@@ -33,6 +33,7 @@ struct DevParams
    float softening;
    float gvx, gvy, gvz;   // uniform gravity
    float max_x, max_y, max_z;
+   int defer_velocity;    // density sweep leaves the velocity part of the force records to k_gather_vel
    // slab mode (one z-slab of the global grid per GPU; all zero / null otherwise)
    int slab;              // 1: slots may be FREE, live count comes from the device cell table
    int gz_global;         // voxel layers of the whole box (binning clamps against this, like the reference)
@@ -147,6 +148,9 @@ struct sphb200_ctx
    float* stage_f;             // N floats: mass staging for upload / download
    bool unsorted_valid;        // rho / acc4 / nbr_count hold the last FULL step, particle order
 
+   cudaStream_t upload_stream;       // sphb200_step_host: velocity upload beside the first half of the step
+   cudaEvent_t upload_ev[2];         // [0] positions on the device, [1] velocities packed
+   cudaEvent_t deferred_vel_event;   // non-null while such a step is being enqueued
    cudaGraphExec_t graph_exec; // one captured step (sph_capi.cu: step_graph), or null
    long long graph_launches;   // kernels per replay
    bool use_graph;             // env SPHB200_NO_GRAPH=1 turns the replay off (A/B)
