@@ -8,20 +8,25 @@
 //   force sweep   : spiky pressure + viscosity (computeAcceleration,
 //                   sph.cpp:778-934) + integrate (937-1022) + wall collision
 //                   (1025-1148) + energy / neighbour statistics
-// A CTA owns an 8x8x4 block of fine cells, stages the block plus its one-cell halo
-// (60 x-contiguous row segments of the cell-sorted arrays) in shared memory, and
-// each thread walks the 9 x-runs of its particle there.
+// Density sweep: a 512-thread CTA owns an 8x8x4 block of fine cells and stages the
+// block plus its one-cell halo (60 x-contiguous row segments of the cell-sorted
+// positions) in shared memory, in groups of four candidates with the coordinates
+// split (SoA inside the group); each thread walks the 9 x-runs of its particle there,
+// two candidates per instruction (packed FP32: fma.rn.f32x2 / add.rn.f32x2, sm_100a).
 //
 // The density sweep has to touch every candidate anyway, so it also records which
 // candidates passed a (slightly enlarged) radius test as a HIT-MASK STREAM: one
-// 8-byte record {32-bit mask, shared-memory byte offset of the chunk's first
-// candidate} per 32-candidate chunk that has a hit.  The force sweep stages the
-// same tile layout and simply walks the set bits of its particle's records -- no
-// second scan -- applying the exact reference test (sph.cpp:633-653) and the pair
-// body in ascending cell order (the order the in-loop viscosity scaling of
-// sph.cpp:880-882 depends on).  No per-particle neighbour list is stored.
+// 8-byte record {32-bit mask, sorted index of the chunk's first candidate} per
+// 32-candidate chunk that has a hit.  The force sweep is flat -- one thread per
+// cell-sorted particle, nothing staged -- and simply walks the set bits of its
+// particle's records: no second scan; it gathers those neighbours through L1 and
+// applies the exact reference test (sph.cpp:633-653) and the pair body in ascending
+// cell order (the order the in-loop viscosity scaling of sph.cpp:880-882 depends on).
+// No per-particle neighbour list is stored.
 // Blocks too dense for shared memory are split (8x8x2, 8x4x2, 4x4x2) and, past
-// that, processed straight from global memory (same arithmetic, scan based).
+// that, processed straight from global memory (scalar arithmetic, scan based).
+// In slab mode (multi-GPU) the force sweep also appends its boundary-layer particles
+// and migrants to the next halo messages (sph_slab_emit, sph_math.cuh).
 #include "sph_math.cuh"
 
 namespace
@@ -582,7 +587,9 @@ __device__ __forceinline__ size_t stream_base(int k)
    return ((size_t)(k >> 5) * WCAP) * 32 + (size_t)(k & 31);
 }
 
-// Density sweep over one (sub-)tile.  STAGED: candidates come from shared memory
+// Scalar density sweep over one (sub-)tile: the fallback for blocks too dense to stage
+// (STAGED = false: candidates from global memory, particles flagged "scan me" for the
+// force sweep).  The staged path is density_targets_packed below.  STAGED: candidates come from shared memory
 // and the hit-mask stream is written; otherwise candidates come from global
 // memory and the particle is flagged "scan me" for the force sweep.
 //
