@@ -72,31 +72,63 @@ __global__ void __launch_bounds__(kThreads)
       int dir = (i & 1) ? -1 : 1;
       int base = 0;
       int windows = (len + 7) / 8;
-      for (int w = 0; w < windows; w++)
+      // The window positions do not depend on what the earlier windows found, only the
+      // stopping rule does: fetch kAhead windows' members and positions at once (16
+      // independent index loads, then 16 independent position loads) and apply the
+      // reference's sequential rules to them.  One thread walks a whole voxel list
+      // serially, so the dependent index -> position round trips are what this kernel
+      // waits for.
+      constexpr int kAhead = 4;
+      for (int w0 = 0; w0 < windows && !done; w0 += kAhead)
       {
-         int first = off + base * dir;
-         if (first < 0 || first + 7 >= len)
-            break;
-         base += 8;
-         for (int j = 0; j < 4; j++)
+         uint32_t q[kAhead][4];
+         float4 pq[kAhead][4];
+         int valid = 0;                      // windows of this batch that pass the range test
+#pragma unroll
+         for (int a = 0; a < kAhead; a++)
          {
-            uint32_t q = idx_sorted[first_member + first + j];
-            if ((int)q == i)
-               continue;
-            float4 pq = pos4[q];
-            float d2 = sph_dist2_exact(pi.x, pi.y, pi.z, pq.x, pq.y, pq.z);
-            if (d2 < P.h2)
+            int first = off + (base + 8 * a) * dir;
+            bool ok = (w0 + a < windows) && valid == a && !(first < 0 || first + 7 >= len);
+            if (ok)
             {
-               out_n[found] = q;
-               out_d[found] = __fmul_rn(__fsqrt_rn(d2), P.scale);
-               found++;
+               valid = a + 1;
+#pragma unroll
+               for (int j = 0; j < 4; j++)
+                  q[a][j] = idx_sorted[first_member + first + j];
             }
          }
-         if (found > E - 8)
+#pragma unroll
+         for (int a = 0; a < kAhead; a++)
+            if (a < valid)
+            {
+#pragma unroll
+               for (int j = 0; j < 4; j++)
+                  pq[a][j] = pos4[q[a][j]];
+            }
+#pragma unroll
+         for (int a = 0; a < kAhead; a++)
          {
-            done = true;
-            break;
+            if (done || a >= valid)
+               break;
+            base += 8;
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+            {
+               if ((int)q[a][j] == i)
+                  continue;
+               float d2 = sph_dist2_exact(pi.x, pi.y, pi.z, pq[a][j].x, pq[a][j].y, pq[a][j].z);
+               if (d2 < P.h2)
+               {
+                  out_n[found] = q[a][j];
+                  out_d[found] = __fmul_rn(__fsqrt_rn(d2), P.scale);
+                  found++;
+               }
+            }
+            if (found > E - 8)
+               done = true;
          }
+         if (valid < kAhead)
+            break;                           // a window fell out of range: this voxel is finished
       }
    }
    nbr_count[i] = found;
