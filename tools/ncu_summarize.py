@@ -10,7 +10,7 @@ tag, steps = sys.argv[1], int(sys.argv[2])
 rows = [r for r in csv.reader(l for l in open("gpurun_out/launches_%s.csv" % tag) if l.startswith('"'))]
 hdr, rows = rows[0], rows[1:]
 ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
-SETUP = ("k_iota", "k_pack_state", "k_unpack_xyz")        # upload / e2e leg, not part of a device-resident step
+SETUP = ("k_iota", "k_pack_state", "k_unpack_xyz", "k_pack_vel", "k_pack_pos", "k_gather_vel")        # upload / e2e leg, not part of a device-resident step
 t = collections.OrderedDict()
 for r in rows:
     name = re.sub(r"\(.*", "", r[ki]).replace("void ", "").replace("<unnamed>::", "")
