@@ -164,8 +164,8 @@ int sphb200_get_launch_count(const sphb200_ctx* ctx, long long* launches);
  * SphParams (grid_z = whole box); particle_count is the slab's slot CAPACITY
  * (owned + ghost particles + headroom for migration).  FULL neighbour mode only.
  * In a slab context sphb200_step() first exchanges migrants and the ghost layer
- * with the z-neighbours (one grouped ncclSend/ncclRecv pair each) and then runs
- * the local step. */
+ * with the z-neighbours (peer puts over NVLink by the force sweep of the previous step,
+ * or one grouped ncclSend/ncclRecv pair each) and then runs the local step. */
 /* 128-byte NCCL unique id (rank 0 makes it, the caller broadcasts it through its
  * own channel, e.g. torch.distributed) */
 int sphb200_comm_unique_id(void* id128);
@@ -189,6 +189,14 @@ int sphb200_slab_step_local(sphb200_ctx* ctx);
 /* ghost particles per halo message.  NCCL ranks agree on the largest request at
  * comm_init; virtual ranks must be given one common value by the caller. */
 int sphb200_slab_set_halo_capacity(sphb200_ctx* ctx, long long ghost_particles);
+/* Put mode for two neighbouring virtual ranks (upper.rank == lower.rank + 1), before their
+ * first exchange: each slab's force sweep then stores its halo particles and migrants
+ * straight into the other's receive buffers (peer memory), which is what real ranks do
+ * over NVLink after sphb200_comm_init (CUDA IPC; SPHB200_HALO=nccl keeps the grouped
+ * ncclSend/ncclRecv instead).  sphb200_slab_transfer becomes a no-op for connected slabs. */
+int sphb200_slab_connect(sphb200_ctx* lower, sphb200_ctx* upper);
+/* 1 when the slab exchanges by peer puts, 0 when by NCCL / sphb200_slab_transfer */
+int sphb200_slab_put_mode(const sphb200_ctx* ctx);
 /* SPHB200_E_CAPACITY when a halo message or the slot capacity overflowed */
 int sphb200_slab_status(sphb200_ctx* ctx);
 

@@ -96,6 +96,8 @@ API = [
     ("sphb200_slab_unpack", [_VP], C.c_int),
     ("sphb200_slab_step_local", [_VP], C.c_int),
     ("sphb200_slab_set_halo_capacity", [_VP, C.c_longlong], C.c_int),
+    ("sphb200_slab_connect", [_VP, _VP], C.c_int),
+    ("sphb200_slab_put_mode", [_VP], C.c_int),
     ("sphb200_slab_status", [_VP], C.c_int),
 ]
 
@@ -475,6 +477,13 @@ class SlabSPH(SPH):
 
     def status(self):
         self._check(self._lib.sphb200_slab_status(self._h))
+
+    def connect_up(self, upper):
+        """Put mode between this virtual rank and the one above it (before the first exchange)."""
+        self._check(self._lib.sphb200_slab_connect(self._h, upper._h))
+
+    def put_mode(self):
+        return bool(self._lib.sphb200_slab_put_mode(self._h))
 
 
 def step_virtual_slabs(slabs, n_steps=1):

@@ -13,10 +13,18 @@
 // FREE slots get a sentinel cell key and fall behind all particles in the sort, so
 // nothing is ever compacted and the live count is read from the cell table on the
 // device (no host round trip per step).  Per step and per neighbour one message
-// {header, migrants, ghost layer} of fixed capacity goes out and one comes in --
-// a single grouped ncclSend/ncclRecv pair over NVLink.  Particles carry their
-// global id; the in-cell order is re-ranked by it (sph_grid.cu) so an N-slab run
-// reproduces the 1-slab run.
+// {header, migrants, ghost layer} goes out and one comes in.  The message is built by
+// the force sweep itself (sph_slab_emit): the kernel that integrates a boundary-layer
+// particle stores it straight into the NEIGHBOUR GPU's receive buffer through a
+// peer-mapped pointer (NVLink; CUDA IPC between the ranks' processes), only the
+// entries that exist cross the link, and a one-thread kernel then publishes the counts
+// and a message number that the neighbour's next exchange waits for.  Receive buffers
+// are double buffered by message parity, which is all the flow control a symmetric
+// per-step exchange needs (see slab_unpack).  Without peer access (or with
+// SPHB200_HALO=nccl) the same messages are built locally and travel as one grouped
+// ncclSend/ncclRecv pair of fixed capacity.  Particles carry their global id; the
+// in-cell order is re-ranked by it (sph_grid.cu) so an N-slab run reproduces the
+// 1-slab run.
 //
 // Exchange rules for an OWNED particle whose voxel layer is now vz:
 //   vz >= z1 : migrant to rank+1; kept here as a GHOST when vz == z1 (it sits in the
@@ -44,12 +52,23 @@ struct SlabComm
    int zlo, zhi;          // local grid [zlo, zhi) = owned + ghost layers
    int mig_cap, ghost_cap;
    size_t msg_bytes;
-   unsigned char* send[2];   // 0: to rank-1 (down), 1: to rank+1 (up)
-   unsigned char* recv[2];   // 0: from rank-1,      1: from rank+1
+   size_t msg_stride;        // msg_bytes rounded up to 256
+   unsigned char* send[2];   // NCCL / copy mode: outgoing messages, 0: to rank-1 (down), 1: to rank+1 (up)
+   unsigned char* recv_area; // one allocation: the four receive buffers [from down / from up][parity]
+   unsigned char* recv[2][2];
+   unsigned* flags;          // [0] / [1]: number of the last complete message from down / up (written by the peer)
+   unsigned* send_cnt;       // message being built: {migrants, ghosts} down, {migrants, ghosts} up
    uint32_t* free_list;      // FREE slot indices of this step
-   unsigned* counters;       // [0] n_free, [1] overflow flag
+   unsigned* counters;       // [0] n_free, [1] error flag: 1 message capacity, 2 slot capacity, 3 peer timeout
    unsigned h_counters[2];
    bool msgs_ready;          // the last force sweep already built the outgoing messages
+   unsigned exchange_no;     // exchanges started so far; message M(e) is consumed by exchange e
+   unsigned build_no;        // number of the message the next emit / finalize works on
+   // put mode: the neighbours' receive buffers and flag words, peer mapped
+   bool put_mode;
+   unsigned char* peer_msg[2][2];   // [0 down / 1 up][parity]
+   unsigned* peer_flag[2];
+   void* ipc_base[2][2];            // what cudaIpcOpenMemHandle returned: [dir][0 receive area, 1 flags]
 };
 
 namespace
@@ -214,6 +233,58 @@ __global__ void __launch_bounds__(kThreads)
    state[slot] = st;
 }
 
+// Publishes the message the previous kernel built: entry counts into its header and -- put
+// mode -- the message number into the neighbour's flag word.  The entries were stored by
+// the previous kernel of this stream, so they are complete (system wide) before this runs.
+__global__ void k_slab_finalize(unsigned char* msg_down, unsigned char* msg_up, const unsigned* __restrict__ send_cnt,
+                                unsigned* flag_down, unsigned* flag_up, unsigned msg_no)
+{
+   if (threadIdx.x != 0 || blockIdx.x != 0)
+      return;
+   if (msg_down)
+   {
+      SlabMsgHeader* h = reinterpret_cast<SlabMsgHeader*>(msg_down);
+      h->n_migrants = send_cnt[0];
+      h->n_ghosts = send_cnt[1];
+   }
+   if (msg_up)
+   {
+      SlabMsgHeader* h = reinterpret_cast<SlabMsgHeader*>(msg_up);
+      h->n_migrants = send_cnt[2];
+      h->n_ghosts = send_cnt[3];
+   }
+   __threadfence_system();
+   if (flag_down)
+      *reinterpret_cast<volatile unsigned*>(flag_down) = msg_no;
+   if (flag_up)
+      *reinterpret_cast<volatile unsigned*>(flag_up) = msg_no;
+}
+
+// put mode: waits until both neighbours have published message `want` (bounded: a peer
+// that never arrives raises error 3 instead of hanging the GPU)
+__global__ void k_slab_wait(const unsigned* flags, int has_down, int has_up, unsigned want, unsigned* counters)
+{
+   if (threadIdx.x != 0 || blockIdx.x != 0)
+      return;
+   const volatile unsigned* f = flags;
+   for (int d = 0; d < 2; d++)
+   {
+      if (!(d ? has_up : has_down))
+         continue;
+      const long long t0 = clock64();
+      while ((int)(f[d] - want) < 0)
+      {
+         if (clock64() - t0 > 6000000000ll)      // ~3 s
+         {
+            atomicMax(&counters[1], 3u);
+            break;
+         }
+         __nanosleep(100);
+      }
+   }
+   __threadfence_system();
+}
+
 __global__ void __launch_bounds__(kThreads)
    k_slab_upload(int capacity, int count, const float* __restrict__ pos_xyz, const float* __restrict__ vel_xyz,
                  const float* __restrict__ mass, const uint32_t* __restrict__ ids, float4* __restrict__ pos4,
@@ -260,6 +331,24 @@ int require_slab(sphb200_ctx* ctx, const char* what)
 
 }  // namespace
 
+// drops the peer mappings of put mode (closing IPC handles of other processes)
+static void slab_disconnect(sphb200_ctx* ctx)
+{
+   SlabComm* c = ctx->comm;
+   for (int d = 0; d < 2; d++)
+   {
+      for (int k = 0; k < 2; k++)
+      {
+         if (c->ipc_base[d][k])
+            cudaIpcCloseMemHandle(c->ipc_base[d][k]);
+         c->ipc_base[d][k] = nullptr;
+      }
+      c->peer_msg[d][0] = c->peer_msg[d][1] = nullptr;
+      c->peer_flag[d] = nullptr;
+   }
+   c->put_mode = false;
+}
+
 // (re)allocates the four message buffers for `ghost_cap` ghost entries per message.
 // Every rank of a run must use the SAME capacity: a send and its matching receive
 // have to agree on the byte count.
@@ -273,16 +362,33 @@ static int slab_alloc_messages(sphb200_ctx* ctx, long long ghost_cap)
    c->ghost_cap = (int)ghost_cap;
    c->mig_cap = (int)(ghost_cap / 4 + 256);
    c->msg_bytes = sizeof(SlabMsgHeader) + sizeof(SlabEntry) * ((size_t)c->ghost_cap + (size_t)c->mig_cap);
+   c->msg_stride = (c->msg_bytes + 255) & ~(size_t)255;
+   slab_disconnect(ctx);           // peer pointers would dangle
    for (int d = 0; d < 2; d++)
    {
       if (c->send[d]) cudaFree(c->send[d]);
-      if (c->recv[d]) cudaFree(c->recv[d]);
-      c->send[d] = c->recv[d] = nullptr;
+      c->send[d] = nullptr;
       SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->send[d], c->msg_bytes));
-      SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->recv[d], c->msg_bytes));
       SPH_CUDA_CHECK(ctx, cudaMemset(c->send[d], 0, sizeof(SlabMsgHeader)));
-      SPH_CUDA_CHECK(ctx, cudaMemset(c->recv[d], 0, sizeof(SlabMsgHeader)));
    }
+   if (c->recv_area) cudaFree(c->recv_area);
+   c->recv_area = nullptr;
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->recv_area, 4 * c->msg_stride));
+   for (int d = 0; d < 2; d++)
+      for (int p = 0; p < 2; p++)
+      {
+         c->recv[d][p] = c->recv_area + (size_t)(2 * d + p) * c->msg_stride;
+         SPH_CUDA_CHECK(ctx, cudaMemset(c->recv[d][p], 0, sizeof(SlabMsgHeader)));
+      }
+   if (!c->flags)
+   {
+      SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->flags, sizeof(unsigned) * 4));
+      SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&c->send_cnt, sizeof(unsigned) * 4));
+   }
+   SPH_CUDA_CHECK(ctx, cudaMemset(c->flags, 0, sizeof(unsigned) * 4));
+   SPH_CUDA_CHECK(ctx, cudaMemset(c->send_cnt, 0, sizeof(unsigned) * 4));
+   c->exchange_no = c->build_no = 0;
+   c->msgs_ready = false;
    return SPHB200_OK;
 }
 
@@ -306,24 +412,42 @@ void sph_comm_dev_params(const sphb200_ctx* ctx, DevParams& P)
    P.has_up = c->rank < c->nranks - 1;
    P.mig_cap = c->mig_cap;
    P.ghost_cap = c->ghost_cap;
-   P.msg_down = c->send[0];
-   P.msg_up = c->send[1];
+   // where the message under construction goes: the neighbour's receive buffer of that
+   // message's parity (put mode), or the local send buffer
+   const int par = (int)(c->build_no & 1u);
+   P.msg_down = P.has_down ? (c->put_mode ? c->peer_msg[0][par] : c->send[0]) : nullptr;
+   P.msg_up = P.has_up ? (c->put_mode ? c->peer_msg[1][par] : c->send[1]) : nullptr;
+   P.send_cnt = c->send_cnt;
    P.comm_counters = c->counters;
 }
 
-// start of a slab's local step: the previous exchange has consumed the outgoing
-// messages; empty them for the force sweep of this step
-int sph_comm_begin_step(sphb200_ctx* ctx)
+// counts into the headers of the message just built and, in put mode, its number into the
+// neighbours' flag words
+static int slab_finalize(sphb200_ctx* ctx)
 {
    SlabComm* c = ctx->comm;
-   for (int d = 0; d < 2; d++)
-      SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->send[d], 0, sizeof(SlabMsgHeader), ctx->stream));
+   DevParams P = sph_dev_params(ctx);
+   k_slab_finalize<<<1, 32, 0, ctx->stream>>>(P.msg_down, P.msg_up, c->send_cnt,
+                                               c->put_mode && P.has_down ? c->peer_flag[0] : nullptr,
+                                               c->put_mode && P.has_up ? c->peer_flag[1] : nullptr, c->build_no);
+   ctx->launches++;
+   SPH_CUDA_CHECK(ctx, cudaGetLastError());
    return SPHB200_OK;
 }
 
-void sph_comm_end_step(sphb200_ctx* ctx)
+// start of a slab's local step: the force sweep of this step builds message exchange_no + 1
+int sph_comm_begin_step(sphb200_ctx* ctx)
+{
+   SlabComm* c = ctx->comm;
+   c->build_no = c->exchange_no + 1;
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->send_cnt, 0, sizeof(unsigned) * 4, ctx->stream));
+   return SPHB200_OK;
+}
+
+int sph_comm_end_step(sphb200_ctx* ctx)
 {
    ctx->comm->msgs_ready = true;
+   return slab_finalize(ctx);
 }
 
 void sph_comm_free(sphb200_ctx* ctx)
@@ -333,11 +457,12 @@ void sph_comm_free(sphb200_ctx* ctx)
       return;
    if (c->has_nccl && c->nccl)
       nccl_api().CommDestroy(c->nccl);
+   slab_disconnect(ctx);
    for (int d = 0; d < 2; d++)
-   {
       if (c->send[d]) cudaFree(c->send[d]);
-      if (c->recv[d]) cudaFree(c->recv[d]);
-   }
+   if (c->recv_area) cudaFree(c->recv_area);
+   if (c->flags) cudaFree(c->flags);
+   if (c->send_cnt) cudaFree(c->send_cnt);
    if (c->free_list) cudaFree(c->free_list);
    if (c->counters) cudaFree(c->counters);
    if (ctx->gid) cudaFree(ctx->gid);
@@ -354,42 +479,67 @@ void sph_comm_free(sphb200_ctx* ctx)
 static int slab_pack(sphb200_ctx* ctx)
 {
    SlabComm* c = ctx->comm;
-   DevParams P = sph_dev_params(ctx);
    cudaStream_t st = ctx->stream;
-   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->counters, 0, sizeof(unsigned), st));   // [1], the overflow flag, is sticky
-   if (ctx->capacity > 0)
+   c->exchange_no++;
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->counters, 0, sizeof(unsigned), st));   // [1], the error flag, is sticky
+   if (c->msgs_ready)
    {
-      if (c->msgs_ready)
+      // message exchange_no was built (and published) by the last force sweep
+      if (ctx->capacity > 0)
+      {
          k_slab_freelist<<<blocks_for(ctx->capacity), kThreads, 0, st>>>(ctx->capacity, ctx->slot_state, c->free_list,
                                                                          c->counters);
-      else
+         ctx->launches++;
+         SPH_CUDA_CHECK(ctx, cudaGetLastError());
+      }
+   }
+   else
+   {
+      c->build_no = c->exchange_no;
+      SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->send_cnt, 0, sizeof(unsigned) * 4, st));
+      DevParams P = sph_dev_params(ctx);
+      if (ctx->capacity > 0)
       {
-         for (int d = 0; d < 2; d++)
-            SPH_CUDA_CHECK(ctx, cudaMemsetAsync(c->send[d], 0, sizeof(SlabMsgHeader), st));
          k_slab_pack<<<blocks_for(ctx->capacity), kThreads, 0, st>>>(P, ctx->capacity, ctx->pos4, ctx->vel4, ctx->gid,
                                                                      ctx->slot_state, c->free_list, c->counters);
+         ctx->launches++;
+         SPH_CUDA_CHECK(ctx, cudaGetLastError());
       }
-      ctx->launches++;
-      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+      int rc = slab_finalize(ctx);
+      if (rc)
+         return rc;
    }
    c->msgs_ready = false;
    return SPHB200_OK;
 }
 
+// Arrivals of message exchange_no into free slots.  Put mode: the messages sit in the
+// receive buffers of parity exchange_no & 1 once both neighbours' flags say so.  Two
+// buffers suffice: a neighbour overwrites this parity again with message e + 2, during its
+// force sweep of step e + 1, which it only reaches after its exchange e + 1 has seen MY
+// message e + 1 -- published after my step e, i.e. after this unpack.
 static int slab_unpack(sphb200_ctx* ctx)
 {
    SlabComm* c = ctx->comm;
+   const int par = c->put_mode ? (int)(c->exchange_no & 1u) : 0;
+   if (c->put_mode)
+   {
+      k_slab_wait<<<1, 32, 0, ctx->stream>>>(c->flags, c->rank > 0, c->rank < c->nranks - 1, c->exchange_no,
+                                             c->counters);
+      ctx->launches++;
+   }
    int max_arrivals = 2 * (c->mig_cap + c->ghost_cap);
    k_slab_unpack<<<blocks_for(max_arrivals), kThreads, 0, ctx->stream>>>(
-      c->mig_cap, c->ghost_cap, c->recv[0], c->recv[1], c->free_list, c->counters, ctx->pos4, ctx->vel4, ctx->gid,
-      ctx->slot_state);
+      c->mig_cap, c->ghost_cap, c->recv[0][par], c->recv[1][par], c->free_list, c->counters, ctx->pos4, ctx->vel4,
+      ctx->gid, ctx->slot_state);
    ctx->launches++;
    SPH_CUDA_CHECK(ctx, cudaGetLastError());
    ctx->voxel_ids_valid = false;
    return SPHB200_OK;
 }
 
-// pack -> one grouped send/recv per neighbour over NCCL -> unpack
+// pack -> (put mode: nothing, the data is already at the neighbour | one grouped
+// send/recv per neighbour over NCCL) -> unpack
 int sph_comm_exchange(sphb200_ctx* ctx)
 {
    SlabComm* c = ctx->comm;
@@ -401,23 +551,93 @@ int sph_comm_exchange(sphb200_ctx* ctx)
    if (rc)
       return rc;
    cudaStream_t st = ctx->stream;
-   if (c->nranks > 1)
+   if (c->nranks > 1 && !c->put_mode)
    {
       NcclApi& N = nccl_api();
       SPH_NCCL_CHECK(ctx, N.GroupStart());
       if (c->rank > 0)
       {
          SPH_NCCL_CHECK(ctx, N.Send(c->send[0], c->msg_bytes, ncclUint8, c->rank - 1, c->nccl, st));
-         SPH_NCCL_CHECK(ctx, N.Recv(c->recv[0], c->msg_bytes, ncclUint8, c->rank - 1, c->nccl, st));
+         SPH_NCCL_CHECK(ctx, N.Recv(c->recv[0][0], c->msg_bytes, ncclUint8, c->rank - 1, c->nccl, st));
       }
       if (c->rank < c->nranks - 1)
       {
          SPH_NCCL_CHECK(ctx, N.Send(c->send[1], c->msg_bytes, ncclUint8, c->rank + 1, c->nccl, st));
-         SPH_NCCL_CHECK(ctx, N.Recv(c->recv[1], c->msg_bytes, ncclUint8, c->rank + 1, c->nccl, st));
+         SPH_NCCL_CHECK(ctx, N.Recv(c->recv[1][0], c->msg_bytes, ncclUint8, c->rank + 1, c->nccl, st));
       }
       SPH_NCCL_CHECK(ctx, N.GroupEnd());
    }
    return slab_unpack(ctx);
+}
+
+// Put mode between the ranks of a real run: every rank exports its receive area and flag
+// words as CUDA IPC handles, neighbours swap them over the NCCL communicator and map them.
+// All ranks end up in the same mode (an allreduce decides).
+static int slab_connect_ipc(sphb200_ctx* ctx)
+{
+   SlabComm* c = ctx->comm;
+   NcclApi& N = nccl_api();
+   const char* env = getenv("SPHB200_HALO");
+   int ok = !(env && strcmp(env, "nccl") == 0);
+   struct Blob { cudaIpcMemHandle_t area, flags; };
+   Blob mine, theirs[2];
+   memset(&mine, 0, sizeof(mine));
+   if (ok && (cudaIpcGetMemHandle(&mine.area, c->recv_area) != cudaSuccess ||
+              cudaIpcGetMemHandle(&mine.flags, c->flags) != cudaSuccess))
+   {
+      cudaGetLastError();
+      ok = 0;
+   }
+   unsigned char* d_blob = nullptr;      // [0] mine, [1] from down, [2] from up, then the vote
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&d_blob, 3 * sizeof(Blob) + sizeof(int)));
+   cudaStream_t st = ctx->stream;
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(d_blob, &mine, sizeof(Blob), cudaMemcpyHostToDevice, st));
+   SPH_NCCL_CHECK(ctx, N.GroupStart());
+   if (c->rank > 0)
+   {
+      SPH_NCCL_CHECK(ctx, N.Send(d_blob, sizeof(Blob), ncclUint8, c->rank - 1, c->nccl, st));
+      SPH_NCCL_CHECK(ctx, N.Recv(d_blob + sizeof(Blob), sizeof(Blob), ncclUint8, c->rank - 1, c->nccl, st));
+   }
+   if (c->rank < c->nranks - 1)
+   {
+      SPH_NCCL_CHECK(ctx, N.Send(d_blob, sizeof(Blob), ncclUint8, c->rank + 1, c->nccl, st));
+      SPH_NCCL_CHECK(ctx, N.Recv(d_blob + 2 * sizeof(Blob), sizeof(Blob), ncclUint8, c->rank + 1, c->nccl, st));
+   }
+   SPH_NCCL_CHECK(ctx, N.GroupEnd());
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(theirs, d_blob + sizeof(Blob), 2 * sizeof(Blob), cudaMemcpyDeviceToHost, st));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+   for (int d = 0; d < 2 && ok; d++)
+   {
+      if (!(d ? c->rank < c->nranks - 1 : c->rank > 0))
+         continue;
+      void *area = nullptr, *flags = nullptr;
+      if (cudaIpcOpenMemHandle(&area, theirs[d].area, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
+          cudaIpcOpenMemHandle(&flags, theirs[d].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
+      {
+         cudaGetLastError();
+         if (area)
+            cudaIpcCloseMemHandle(area);
+         ok = 0;
+         break;
+      }
+      c->ipc_base[d][0] = area;
+      c->ipc_base[d][1] = flags;
+      // my message to the neighbour below arrives there as "from up" (index 1), and vice versa
+      for (int p = 0; p < 2; p++)
+         c->peer_msg[d][p] = static_cast<unsigned char*>(area) + (size_t)(2 * (1 - d) + p) * c->msg_stride;
+      c->peer_flag[d] = static_cast<unsigned*>(flags) + (1 - d);
+   }
+   int* d_vote = reinterpret_cast<int*>(d_blob + 3 * sizeof(Blob));
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(d_vote, &ok, sizeof(int), cudaMemcpyHostToDevice, st));
+   SPH_NCCL_CHECK(ctx, N.AllReduce(d_vote, d_vote, 1, ncclInt32, ncclMin, c->nccl, st));
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(&ok, d_vote, sizeof(int), cudaMemcpyDeviceToHost, st));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+   cudaFree(d_blob);
+   if (ok)
+      c->put_mode = true;
+   else
+      slab_disconnect(ctx);
+   return SPHB200_OK;
 }
 
 extern "C" {
@@ -503,7 +723,57 @@ int sphb200_comm_init(sphb200_ctx* ctx, int rank, int nranks, const void* id128,
    }
    else if (nranks == 1)
       c->has_nccl = true, c->nccl = nullptr;   // single slab: nothing to exchange
-   return slab_alloc_messages(ctx, gcap);
+   rc = slab_alloc_messages(ctx, gcap);
+   if (rc)
+      return rc;
+   if (c->has_nccl && c->nccl)
+      return slab_connect_ipc(ctx);
+   return SPHB200_OK;
+}
+
+// Virtual ranks (one process): wires two neighbouring slabs for put mode -- each one's
+// force sweep then writes straight into the other's receive buffers, as between GPUs.
+int sphb200_slab_connect(sphb200_ctx* lower, sphb200_ctx* upper)
+{
+   int rc = require_slab(lower, "slab_connect");
+   if (rc)
+      return rc;
+   rc = require_slab(upper, "slab_connect");
+   if (rc)
+      return rc;
+   SlabComm *a = lower->comm, *b = upper->comm;
+   if (b->rank != a->rank + 1 || a->msg_bytes != b->msg_bytes)
+      return sph_fail(lower, SPHB200_E_INVALID, "slab_connect: contexts are not neighbours with equal halo capacity");
+   if (a->exchange_no || b->exchange_no)
+      return sph_fail(lower, SPHB200_E_INVALID, "slab_connect: connect before the first exchange");
+   if (lower->device != upper->device)
+   {
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, lower->device, upper->device);
+      if (!can)
+         return sph_fail(lower, SPHB200_E_COMM, "slab_connect: no peer access between the two devices");
+      cudaSetDevice(lower->device);
+      cudaDeviceEnablePeerAccess(upper->device, 0);
+      cudaSetDevice(upper->device);
+      cudaDeviceEnablePeerAccess(lower->device, 0);
+      cudaGetLastError();      // already enabled is fine
+   }
+   for (int p = 0; p < 2; p++)
+   {
+      a->peer_msg[1][p] = b->recv[0][p];     // lower's "up" message arrives at upper as "from down"
+      b->peer_msg[0][p] = a->recv[1][p];
+   }
+   a->peer_flag[1] = b->flags + 0;
+   b->peer_flag[0] = a->flags + 1;
+   // a slab is in put mode once every neighbour it has is wired
+   a->put_mode = (a->rank == 0 || a->peer_flag[0]) && a->peer_flag[1];
+   b->put_mode = b->peer_flag[0] && (b->rank == b->nranks - 1 || b->peer_flag[1]);
+   return SPHB200_OK;
+}
+
+int sphb200_slab_put_mode(const sphb200_ctx* ctx)
+{
+   return ctx && ctx->comm && ctx->comm->put_mode ? 1 : 0;
 }
 
 // virtual ranks (no communicator) cannot negotiate: the caller gives every slab the
@@ -660,12 +930,14 @@ int sphb200_slab_transfer(sphb200_ctx* src, int dir, sphb200_ctx* dst)
    if (dir < 0 || dir > 1 || src->comm->msg_bytes != dst->comm->msg_bytes ||
        dst->comm->rank != src->comm->rank + (dir ? 1 : -1))
       return sph_fail(src, SPHB200_E_INVALID, "slab_transfer: contexts are not neighbours in that direction");
+   if (src->comm->put_mode || dst->comm->put_mode)
+      return SPHB200_OK;      // connected slabs: the message is already in dst's receive buffer
    // the message is complete once src's stream has drained; the copy is ordered on dst's
    // stream (after dst's last unpack, before its next one).  A plain cudaMemcpy would not
    // do: device-to-device copies return before they finish and the contexts' non-blocking
    // streams do not wait for the legacy stream.
    SPH_CUDA_CHECK(src, cudaStreamSynchronize(src->stream));
-   SPH_CUDA_CHECK(dst, cudaMemcpyAsync(dst->comm->recv[1 - dir], src->comm->send[dir], src->comm->msg_bytes,
+   SPH_CUDA_CHECK(dst, cudaMemcpyAsync(dst->comm->recv[1 - dir][0], src->comm->send[dir], src->comm->msg_bytes,
                                        cudaMemcpyDefault, dst->stream));
    SPH_CUDA_CHECK(dst, cudaStreamSynchronize(dst->stream));   // src may repack its send buffer right away
    return SPHB200_OK;
@@ -709,6 +981,8 @@ int sphb200_slab_status(sphb200_ctx* ctx)
                                                "(raise SPHB200_HALO_CAPACITY)");
    if (c->h_counters[1] == 2)
       return sph_fail(ctx, SPHB200_E_CAPACITY, "slab exchange: no free particle slot left (raise particle_count)");
+   if (c->h_counters[1] == 3)
+      return sph_fail(ctx, SPHB200_E_COMM, "slab exchange: a neighbour's halo message did not arrive (peer timeout)");
    return SPHB200_OK;
 }
 

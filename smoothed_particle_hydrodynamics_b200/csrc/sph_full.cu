@@ -1060,6 +1060,13 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
       if (k < sph_live_count(P))
       {
          o = idx_sorted[k];
+         if (!active)
+         {
+            // ghosts and particles in transit are not integrated here: defined outputs
+            // instead of whatever an earlier step left at this sorted position
+            s_count[k] = 0;
+            s_acc4[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+         }
          if (!active && P.slot_state[o] == SLOT_OWNED)
          {
             // an owned particle parked in a ghost layer (it crossed more than one slab in a
@@ -1174,15 +1181,20 @@ int sph_full_tile_count(const sphb200_ctx* ctx)
 
 int sph_step_full(sphb200_ctx* ctx)
 {
+   // slab mode: the force sweep of this step builds the next halo messages; their number
+   // (and with it the destination buffers in DevParams) is fixed first
+   if (ctx->comm)
+   {
+      int rc0 = sph_comm_begin_step(ctx);
+      if (rc0)
+         return rc0;
+   }
    DevParams P = sph_dev_params(ctx);
    const int n = ctx->n_local;
    cudaStream_t st = ctx->stream;
    const bool timed = ctx->params.enable_timers != 0;
    if (timed) cudaEventRecord(ctx->ev[0], st);
-   int rc = ctx->comm ? sph_comm_begin_step(ctx) : SPHB200_OK;
-   if (rc)
-      return rc;
-   rc = sph_bin_and_sort(ctx, true);
+   int rc = sph_bin_and_sort(ctx, true);
    if (rc)
       return rc;
    if (timed) cudaEventRecord(ctx->ev[1], st);
@@ -1237,7 +1249,11 @@ int sph_step_full(sphb200_ctx* ctx)
       return rc;
    if (timed) cudaEventRecord(ctx->ev[6], st);
    if (ctx->comm)
-      sph_comm_end_step(ctx);
+   {
+      rc = sph_comm_end_step(ctx);
+      if (rc)
+         return rc;
+   }
    ctx->lists_valid = false;
    ctx->snapshot_valid = true;
    ctx->unsorted_valid = false;

@@ -46,9 +46,10 @@ struct DevParams
    int own_z0, own_z1;                // owned voxel layers (global layer indices)
    int has_down, has_up;              // neighbour ranks present
    int mig_cap, ghost_cap;            // message capacities (entries)
-   unsigned char* msg_down;           // to rank - 1
+   unsigned char* msg_down;           // to rank - 1: local send buffer, or the neighbour's receive buffer (peer mapped)
    unsigned char* msg_up;             // to rank + 1
-   unsigned* comm_counters;           // [0] free slots of this exchange, [1] overflow flag
+   unsigned* send_cnt;                // entries so far: {migrants, ghosts} down, {migrants, ghosts} up
+   unsigned* comm_counters;           // [0] free slots of this exchange, [1] error flag
 };
 
 // SLOT_LEAVING_*: an OWNED particle the force sweep has already put into a migrant
@@ -191,7 +192,7 @@ int sph_finish_scalars(sphb200_ctx* ctx, int blocks);
 // sph_comm.cu
 int sph_comm_exchange(sphb200_ctx* ctx);
 int sph_comm_begin_step(sphb200_ctx* ctx);
-void sph_comm_end_step(sphb200_ctx* ctx);
+int sph_comm_end_step(sphb200_ctx* ctx);
 void sph_comm_free(sphb200_ctx* ctx);
 void sph_comm_dev_params(const sphb200_ctx* ctx, DevParams& P);
 int sph_grid_alloc(sphb200_ctx* ctx);

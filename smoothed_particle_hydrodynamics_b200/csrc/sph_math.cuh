@@ -258,28 +258,28 @@ __device__ __forceinline__ unsigned char sph_slab_emit(const DevParams& P, bool 
    const bool migrant = mig_up || mig_down;
    const bool ghost_up = owned && !migrant && vz == P.own_z1 - 1 && P.has_up;
    const bool ghost_down = owned && !migrant && vz == P.own_z0 && P.has_down;   // 1-layer slabs ghost both ways
-   SlabMsgHeader* hu = reinterpret_cast<SlabMsgHeader*>(P.msg_up);
-   SlabMsgHeader* hd = reinterpret_cast<SlabMsgHeader*>(P.msg_down);
+   // slots come from this rank's own counters (k_slab_finalize publishes them); the entries
+   // go wherever the message lives -- in put mode that is the neighbour GPU's memory
    SlabEntry e;
    e.pos = pos;
    e.vel = vel_gid;
    bool overflow = false;
-   unsigned s = sph_warp_append(&hu->n_migrants, mig_up);
+   unsigned s = sph_warp_append(&P.send_cnt[2], mig_up);
    if (mig_up)
    {
       if (s < (unsigned)P.mig_cap) sph_msg_entries(P.msg_up)[s] = e; else overflow = true;
    }
-   s = sph_warp_append(&hd->n_migrants, mig_down);
+   s = sph_warp_append(&P.send_cnt[0], mig_down);
    if (mig_down)
    {
       if (s < (unsigned)P.mig_cap) sph_msg_entries(P.msg_down)[s] = e; else overflow = true;
    }
-   s = sph_warp_append(&hu->n_ghosts, ghost_up);
+   s = sph_warp_append(&P.send_cnt[3], ghost_up);
    if (ghost_up)
    {
       if (s < (unsigned)P.ghost_cap) sph_msg_entries(P.msg_up)[P.mig_cap + s] = e; else overflow = true;
    }
-   s = sph_warp_append(&hd->n_ghosts, ghost_down);
+   s = sph_warp_append(&P.send_cnt[1], ghost_down);
    if (ghost_down)
    {
       if (s < (unsigned)P.ghost_cap) sph_msg_entries(P.msg_down)[P.mig_cap + s] = e; else overflow = true;

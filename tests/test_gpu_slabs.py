@@ -33,8 +33,12 @@ def _gather(slabs, field):
     return vals[order], gids[order]
 
 
+@pytest.mark.parametrize("mode", ["put", "copy"])
 @pytest.mark.parametrize("nranks", [2, 4])
-def test_virtual_slabs_reproduce_single_gpu_run(nranks):
+def test_virtual_slabs_reproduce_single_gpu_run(nranks, mode):
+    """mode "put": neighbouring slabs are connected, the force sweep stores its halo particles and
+    migrants straight into the neighbour's receive buffers (what real ranks do over NVLink);
+    "copy": messages are built locally and moved by sphb200_slab_transfer (the NCCL path's data flow)."""
     cfg = dict(scenes.CONFIGS["dambreak_128k"])
     cfg["grid"] = (40, 16, 32)          # deeper box: the block moves along z as well
     nx, ny, nz = cfg["sites"]
@@ -59,6 +63,10 @@ def test_virtual_slabs_reproduce_single_gpu_run(nranks):
         own = np.flatnonzero((vz >= z0) & (vz < z1))
         s.upload_slab(pos[own], vel[own], mass[own], own.astype(np.uint32))
         slabs.append(s)
+    if mode == "put":
+        for lo, hi in zip(slabs[:-1], slabs[1:]):
+            lo.connect_up(hi)
+    assert all(s.put_mode() == (mode == "put") for s in slabs)
     owned0 = [s.local_count()[0] for s in slabs]
     assert sum(owned0) == n
 
