@@ -336,6 +336,8 @@ def run_ours(args):
                    "neighbor_pairs_per_sec": pairs_last / (ms_per_step * 1e-3),
                    "mean_neighbors": pairs_last / n_total,
                    "l2": "inputs (>= 512 MB of state per GPU) larger than the 126 MB L2",
+                   "halo": ("peer puts by the force sweep (CUDA IPC / NVLink)" if sph.put_mode() else
+                            "grouped ncclSend/ncclRecv") if slab and world > 1 else None,
                    "step_alg_bytes_per_particle": ALG_BYTES_STEP,
                    "step_hbm_frac": ALG_BYTES_STEP * n_dev / (ms_per_step * 1e-3) / 1e9 / hbm,
                    "phase_ms_rank0": {"exchange_bin_sort_gather": float(phase[0]), "density_eos": dens_ms,
