@@ -253,6 +253,9 @@ __device__ __forceinline__ unsigned sph_block_append(unsigned* counter, bool wan
 __device__ __forceinline__ unsigned char sph_slab_emit(const DevParams& P, bool owned, float4 pos, float4 vel_gid)
 {
    const int vz = sph_voxel_coord(pos.z, P.h_times2_inv, P.gz_global);
+   // almost every warp is far from the slab faces: one vote instead of four appends
+   if (!__any_sync(0xffffffffu, owned && (vz >= P.own_z1 - 1 || vz <= P.own_z0)))
+      return SLOT_OWNED;
    const bool mig_up = owned && vz >= P.own_z1 && P.has_up;
    const bool mig_down = owned && !mig_up && vz < P.own_z0 && P.has_down;
    const bool migrant = mig_up || mig_down;
