@@ -254,7 +254,7 @@ __device__ __forceinline__ unsigned char sph_slab_emit(const DevParams& P, bool 
 {
    const int vz = sph_voxel_coord(pos.z, P.h_times2_inv, P.gz_global);
    // almost every warp is far from the slab faces: one vote instead of four appends
-   if (!__any_sync(0xffffffffu, owned && (vz >= P.own_z1 - 1 || vz <= P.own_z0)))
+   if (!__any_sync(0xffffffffu, owned && ((P.has_up && vz >= P.own_z1 - 1) || (P.has_down && vz <= P.own_z0))))
       return SLOT_OWNED;
    const bool mig_up = owned && vz >= P.own_z1 && P.has_up;
    const bool mig_down = owned && !mig_up && vz < P.own_z0 && P.has_down;
