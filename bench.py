@@ -250,6 +250,7 @@ def run_ours(args):
     # ---- device-resident throughput ----------------------------------------
     sampler = ClockSampler(local)
     sampler.start()
+    barrier()            # every rank has its scene on the device before the first exchange
     sph.step_n(args.warmup)
     barrier()
     l0 = sph.launch_count()
@@ -358,6 +359,7 @@ def run_ours(args):
         out["cpu_baseline"] = cpu_reference_sample(steps=10, warmup=1)
     if rank == 0:
         emit(out)
+    barrier()            # peer-put halos: no rank frees its receive buffers while a neighbour may still write
     sph.close()
     if world > 1:
         dist.destroy_process_group()

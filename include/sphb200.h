@@ -195,6 +195,8 @@ int sphb200_slab_set_halo_capacity(sphb200_ctx* ctx, long long ghost_particles);
  * over NVLink after sphb200_comm_init (CUDA IPC; SPHB200_HALO=nccl keeps the grouped
  * ncclSend/ncclRecv instead).  sphb200_slab_transfer becomes a no-op for connected slabs. */
 int sphb200_slab_connect(sphb200_ctx* lower, sphb200_ctx* upper);
+/* In put mode a slab's receive buffers are written by its neighbours: destroy the contexts
+ * of a run together (after a barrier of the caller's), not while a neighbour still steps. */
 /* 1 when the slab exchanges by peer puts, 0 when by NCCL / sphb200_slab_transfer */
 int sphb200_slab_put_mode(const sphb200_ctx* ctx);
 /* SPHB200_E_CAPACITY when a halo message or the slot capacity overflowed */

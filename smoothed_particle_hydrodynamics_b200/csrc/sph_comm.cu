@@ -274,7 +274,7 @@ __global__ void k_slab_wait(const unsigned* flags, int has_down, int has_up, uns
       const long long t0 = clock64();
       while ((int)(f[d] - want) < 0)
       {
-         if (clock64() - t0 > 6000000000ll)      // ~3 s
+         if (clock64() - t0 > 40000000000ll)     // ~20 s
          {
             atomicMax(&counters[1], 3u);
             break;
