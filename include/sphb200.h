@@ -173,7 +173,9 @@ int sphb200_comm_unique_id(void* id128);
  * one process (even on one GPU) exchanged through sphb200_slab_transfer */
 int sphb200_comm_init(sphb200_ctx* ctx, int rank, int nranks, const void* id128, int z0, int z1);
 int sphb200_get_local_count(const sphb200_ctx* ctx, int* owned, int* ghosts);
-/* `count` owned particles with their global ids; the remaining slots are free */
+/* `count` owned particles with their global ids; the remaining slots are free.  Collective:
+ * every rank of a run uploads at the same point of its step sequence (a halo message built
+ * from the old state is retired by number on all ranks alike). */
 int sphb200_upload_slab(sphb200_ctx* ctx, int count, const float* pos_xyz, const float* vel_xyz,
                         const float* mass, const uint32_t* global_ids);
 /* owned particles only, compacted, with their global ids (any order).  Fields:

@@ -851,6 +851,11 @@ int sphb200_upload_slab(sphb200_ctx* ctx, int count, const float* pos_xyz, const
       for (int i = 0; i < count && ctx->uniform_mass; i++)
          ctx->uniform_mass = mass[i] == 1.0f;
    ctx->n_owned = count;
+   // A message built from the old state may already be published at the neighbours (put
+   // mode): retire its number so that nobody consumes it.  Uploads are collective: every
+   // rank of a run uploads at the same point of its step sequence.
+   if (ctx->comm->msgs_ready)
+      ctx->comm->exchange_no++;
    ctx->comm->msgs_ready = false;
    SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->comm->counters, 0, sizeof(unsigned) * 2, st));
    ctx->lists_valid = false;
