@@ -288,13 +288,16 @@ __global__ void k_slab_wait(const unsigned* flags, int has_down, int has_up, uns
 __global__ void __launch_bounds__(kThreads)
    k_slab_upload(int capacity, int count, const float* __restrict__ pos_xyz, const float* __restrict__ vel_xyz,
                  const float* __restrict__ mass, const uint32_t* __restrict__ ids, float4* __restrict__ pos4,
-                 float4* __restrict__ vel4, uint32_t* __restrict__ gid, unsigned char* __restrict__ state)
+                 float4* __restrict__ vel4, uint32_t* __restrict__ gid, unsigned char* __restrict__ state,
+                 int* __restrict__ mass_not_one)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= capacity)
       return;
    if (i < count)
    {
+      if (mass && mass[i] != 1.0f)
+         *mass_not_one = 1;      // benign race: every writer stores the same value
       pos4[i] = make_float4(pos_xyz[3 * (size_t)i], pos_xyz[3 * (size_t)i + 1], pos_xyz[3 * (size_t)i + 2],
                             mass ? mass[i] : 1.0f);
       vel4[i] = make_float4(vel_xyz[3 * (size_t)i], vel_xyz[3 * (size_t)i + 1], vel_xyz[3 * (size_t)i + 2], 0.0f);
@@ -836,20 +839,24 @@ int sphb200_upload_slab(sphb200_ctx* ctx, int count, const float* pos_xyz, const
       if (mass)
          SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->stage_f, mass, sizeof(float) * (size_t)count, cudaMemcpyHostToDevice, st));
    }
+   // migrants bring their own masses: the uniform-mass fast path is only safe when
+   // every rank uploads unit masses (the reference's only value, sph.cpp:88); checked on the
+   // device while packing
+   ctx->uniform_mass = true;
    if (ctx->capacity > 0)
    {
+      int* d_flag = &ctx->d_scalars->overflow;   // free between steps
+      SPH_CUDA_CHECK(ctx, cudaMemsetAsync(d_flag, 0, sizeof(int), st));
       k_slab_upload<<<blocks_for(ctx->capacity), kThreads, 0, st>>>(ctx->capacity, count, d_pos, d_vel,
                                                                     mass ? ctx->stage_f : nullptr, d_ids, ctx->pos4,
-                                                                    ctx->vel4, ctx->gid, ctx->slot_state);
+                                                                    ctx->vel4, ctx->gid, ctx->slot_state, d_flag);
       ctx->launches++;
       SPH_CUDA_CHECK(ctx, cudaGetLastError());
+      int not_one = 0;
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(&not_one, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+      SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(st));
+      ctx->uniform_mass = not_one == 0;
    }
-   // migrants bring their own masses: the uniform-mass fast path is only safe when
-   // every rank uploads unit masses (the reference's only value, sph.cpp:88)
-   ctx->uniform_mass = true;
-   if (mass)
-      for (int i = 0; i < count && ctx->uniform_mass; i++)
-         ctx->uniform_mass = mass[i] == 1.0f;
    ctx->n_owned = count;
    // A message built from the old state may already be published at the neighbours (put
    // mode): retire its number so that nobody consumes it.  Uploads are collective: every
