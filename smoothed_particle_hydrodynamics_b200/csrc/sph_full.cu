@@ -34,6 +34,12 @@ namespace
 
 // Tile shape, CTA size and staging capacity.  Overridable at compile time for A/B runs
 // (tools/build_variant.py); the defaults are the measured best (profiles/r01_history.md).
+#ifndef SPH_DENS_SPLIT_ACC
+#define SPH_DENS_SPLIT_ACC 0     // 1: separate poly6 accumulators for the two halves of a group (A/B)
+#endif
+#ifndef SPH_DENS_UNROLL
+#define SPH_DENS_UNROLL 3        // unroll factor of the loop over the 9 runs: 3 = one z-plane per trip (1: 2.28 ms, 3: 2.24, 9: 2.37)
+#endif
 #ifndef SPH_TBY
 #define SPH_TBY 8
 #endif
@@ -49,6 +55,7 @@ namespace
 #ifndef SPH_CAP
 #define SPH_CAP 6600
 #endif
+constexpr int kDensUnroll = SPH_DENS_UNROLL;
 constexpr int TBX = 8, TBY = SPH_TBY, TBZ = SPH_TBZ;   // tile extent in fine cells (x rows are contiguous in memory)
 constexpr int HROWS = (TBY + 2) * (TBZ + 2);   // halo rows (y,z) of a full tile
 constexpr int CSW = TBX + 3;                // cell_start entries per halo row
@@ -741,7 +748,7 @@ __device__ __forceinline__ ulonglong2 lds128(unsigned addr)
 // starts OFF bytes from shared address `a`
 template <bool UNIT, bool UMASS, int OFF>
 __device__ __forceinline__ void density_group(unsigned a, f32x2 NX, f32x2 NY, f32x2 NZ, f32x2 NH, f32x2 NTHR,
-                                              f32x2 S2, unsigned& mask, f32x2& sum2)
+                                              f32x2 S2, unsigned& mask, f32x2& sum2, f32x2& sum2b)
 {
    const ulonglong2 X = lds128<OFF>(a), Y = lds128<OFF + 16>(a), Z = lds128<OFF + 32>(a);
    ulonglong2 M;
@@ -764,10 +771,11 @@ __device__ __forceinline__ void density_group(unsigned a, f32x2 NX, f32x2 NY, f3
       mask = __funnelshift_l(__float_as_uint(s1), mask, 1);
       unpack2(ee, e0, e1);
       f32x2 u = pack2(fminf(e0, 0.0f), fminf(e1, 0.0f));
+      f32x2& acc = (SPH_DENS_SPLIT_ACC && half) ? sum2b : sum2;
       if (UMASS)
-         sum2 = ffma2(fmul2(u, u), u, sum2);
+         acc = ffma2(fmul2(u, u), u, acc);
       else
-         sum2 = ffma2(fmul2(half ? M.y : M.x, u), fmul2(u, u), sum2);
+         acc = ffma2(fmul2(half ? M.y : M.x, u), fmul2(u, u), acc);
    }
 }
 
@@ -792,12 +800,12 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
       const float4 pi = __ldg(&s_pos4[T.k]);
       const f32x2 NX = pack2(-pi.x, -pi.x), NY = pack2(-pi.y, -pi.y), NZ = pack2(-pi.z, -pi.z);
       uint2* rec = hit_rec + stream_base(T.k);
-      f32x2 sum2 = pack2(0.0f, 0.0f);
+      f32x2 sum2 = pack2(0.0f, 0.0f), sum2b = pack2(0.0f, 0.0f);
       int nw = 0, nhits = 0;
       // the 9 runs in ascending row order: (z-1: y-1, y, y+1), (z: ...), (z+1: ...)
       const int* csp = &L.cs[T.hr0 - rowstep - 1][T.lx - 1];
       const int* dlp = &L.row_delta[T.hr0 - rowstep - 1];
-#pragma unroll 1
+#pragma unroll kDensUnroll
       for (int r = 0; r < 9; r++)
       {
          const int delta = dlp[0];
@@ -816,7 +824,7 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
             // fewer groups drop out and the warp reconverges once (a fall-through switch
             // would serialise the lanes by entry point).
             unsigned mask = 0;
-#define SPH_GROUP(N) density_group<UNIT, UMASS, (N) * GF * 4>(a0, NX, NY, NZ, NH, NTHR, S2, mask, sum2)
+#define SPH_GROUP(N) density_group<UNIT, UMASS, (N) * GF * 4>(a0, NX, NY, NZ, NH, NTHR, S2, mask, sum2, sum2b)
             SPH_GROUP(0);
             if (ng > 1)
             {
@@ -861,7 +869,7 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
       }
       hit_info[T.k] = nw <= WCAP ? ((unsigned)nw | ((unsigned)nhits << 8)) : kNoStream;
       float sa, sb;
-      unpack2(sum2, sa, sb);
+      unpack2(SPH_DENS_SPLIT_ACC ? fadd2(sum2, sum2b) : sum2, sa, sb);
       const float sum = -(sa + sb);
       // the particle itself sat in the centre run with e = -hs2: remove its own term (the
       // reference skips realIndex == particleIndex, sph.cpp:737); a NaN position has term 0
