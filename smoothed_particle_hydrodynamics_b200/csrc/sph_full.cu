@@ -34,6 +34,16 @@ namespace
 
 // Tile shape, CTA size and staging capacity.  Overridable at compile time for A/B runs
 // (tools/build_variant.py); the defaults are the measured best (profiles/r01_history.md).
+#ifndef SPH_STREAM_HINTS
+#define SPH_STREAM_HINTS 0       // 1: read-once / write-once data bypasses L1 allocation (ld.cs / st.cs) (A/B)
+#endif
+#if SPH_STREAM_HINTS
+#define SPH_LD_ONCE(p) __ldcs(p)
+#define SPH_ST_ONCE(p, v) __stcs(p, v)
+#else
+#define SPH_LD_ONCE(p) __ldg(p)
+#define SPH_ST_ONCE(p, v) (*(p) = (v))
+#endif
 #ifndef SPH_DENS_SPLIT_ACC
 #define SPH_DENS_SPLIT_ACC 0     // 1: separate poly6 accumulators for the two halves of a group (A/B)
 #endif
@@ -305,10 +315,10 @@ __device__ __forceinline__ void force_store(const DevParams& P, int k, const For
    uint32_t o = idx_sorted[k];
    new_pos = make_float4(r[0], r[1], r[2], mass);
    new_vel = make_float4(v[0], v[1], v[2], 0.0f);
-   pos4[o] = new_pos;
-   vel4[o] = new_vel;
-   s_acc4[k] = make_float4(a.x, a.y, a.z, 0.0f);
-   s_count[k] = count;
+   SPH_ST_ONCE(&pos4[o], new_pos);
+   SPH_ST_ONCE(&vel4[o], new_vel);
+   SPH_ST_ONCE(&s_acc4[k], make_float4(a.x, a.y, a.z, 0.0f));
+   SPH_ST_ONCE(&s_count[k], count);
    ek = e_kin;
    ep = e_pot;
 }
@@ -861,13 +871,13 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
             if (mask != 0u)
             {
                if (nw < WCAP)
-                  rec[(size_t)nw * 32] = make_uint2(mask, (unsigned)(c0 - delta));
+                  SPH_ST_ONCE(&rec[(size_t)nw * 32], make_uint2(mask, (unsigned)(c0 - delta)));
                nw++;
                nhits += __popc(mask);
             }
          }
       }
-      hit_info[T.k] = nw <= WCAP ? ((unsigned)nw | ((unsigned)nhits << 8)) : kNoStream;
+      SPH_ST_ONCE(&hit_info[T.k], nw <= WCAP ? ((unsigned)nw | ((unsigned)nhits << 8)) : kNoStream);
       float sa, sb;
       unpack2(SPH_DENS_SPLIT_ACC ? fadd2(sum2, sum2b) : sum2, sa, sb);
       const float sum = -(sa + sb);
@@ -970,10 +980,10 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    unsigned long long cnt = 0;
    int cmax = -1, cmin = 0x7fffffff;
    // per-particle operands and the records: independent loads, issued together
-   const unsigned info = active ? hit_info[kk] : 0u;
+   const unsigned info = active ? SPH_LD_ONCE(&hit_info[kk]) : 0u;
    const float4 pi = s_posA4[kk];
    const float4 vi = s_velB4[kk];
-   const float rho_i = s_rho[kk];
+   const float rho_i = SPH_LD_ONCE(&s_rho[kk]);
    const bool scan = (info & 0xffu) == kNoStream;
    const int nw = scan ? 0 : (int)(info & 0xffu);
    const int nhits = scan ? 0 : (int)(info >> 8);
@@ -981,7 +991,7 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
 #pragma unroll 4
    for (int w = 0; w < min(nw, RSM); w++)
    {
-      uint2 r2 = __ldg(rec + (size_t)w * 32);
+      uint2 r2 = SPH_LD_ONCE(rec + (size_t)w * 32);
       rmask[w * kForceThreads] = r2.x;
       rbase[w * kForceThreads] = r2.y;
    }
@@ -1002,7 +1012,7 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
          }
          else
          {
-            uint2 r2 = __ldg(rec + (size_t)w * 32);
+            uint2 r2 = SPH_LD_ONCE(rec + (size_t)w * 32);
             m = r2.x;
             base = (int)r2.y;
          }
