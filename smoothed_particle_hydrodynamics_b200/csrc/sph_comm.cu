@@ -786,6 +786,10 @@ int sphb200_slab_set_halo_capacity(sphb200_ctx* ctx, long long ghost_particles)
    int rc = require_slab(ctx, "slab_set_halo_capacity");
    if (rc)
       return rc;
+   if (ctx->comm->nccl)
+      return sph_fail(ctx, SPHB200_E_INVALID, "slab_set_halo_capacity: ranks with a communicator agree on the "
+                                              "capacity at comm_init (SPHB200_HALO_CAPACITY); their neighbours "
+                                              "hold mappings of the receive buffers");
    SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
    SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
    return slab_alloc_messages(ctx, ghost_particles);
