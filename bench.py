@@ -41,7 +41,7 @@ ALG_BYTES_FORCE = 72.0     # force+integrate+collide sweep: R(16+16+4) + W(16+16
 ALG_BYTES_DENSITY = 20.0   # density+EOS sweep: R16 + W4
 # dram__bytes_read.sum + dram__bytes_write.sum per launch at 16.7M particles, from the committed
 # `ncu --set full` capture (profiles/r01_ncu_top_kernels_16m.csv)
-NCU_TRAFFIC_16M = {"density": 0.869e9 + 1.554e9, "force": 2.010e9 + 0.851e9}
+NCU_TRAFFIC_16M = {"density": 0.870e9 + 1.554e9, "force": 2.010e9 + 0.852e9}
 NU = 40.0
 
 
@@ -293,8 +293,8 @@ def run_ours(args):
     else:
         dom = {"key": "density", "ms": dens_ms, "bytes": ALG_BYTES_DENSITY,
                "kernel": "k_density_tiled (density + EOS + hit-mask stream sweep, packed FP32)",
-               "note": "FP32 pipe / issue bound (ncu: FMA pipe 57% of active cycles at 2 cycles per packed "
-                       "instruction, DRAM 6% busy), not HBM bound: DESIGN.md section 5"}
+               "note": "FP32 pipe / issue bound (ncu: FMA pipe 61% of active cycles at 2 cycles per packed "
+                       "instruction, DRAM 13% busy), not HBM bound: DESIGN.md section 5"}
     achieved = dom["bytes"] * n_dev / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
 
     # ---- end to end through host buffers -------------------------------------
