@@ -76,7 +76,10 @@ constexpr int kCap = SPH_CAP;               // staged particles per (sub-)tile, 
 constexpr int kCapMass = (12 * (kCap + 4)) / 16 - 4;   // ... with per-particle masses (16 B each): same bytes
 constexpr int WCAP = 32;                    // hit-mask records per particle (32 candidates each)
 constexpr unsigned kNoStream = 0xffu;       // info.nw value: no stream, scan instead
-constexpr int RSM = 16;                     // records per thread kept in shared memory by the force sweep
+#ifndef SPH_FORCE_RSM
+#define SPH_FORCE_RSM 10   // 16: 2.49 ms, 12: 2.42, 10 and 8: 2.41, 6: 2.47, 4: 2.56 -- shared memory given up here is L1 for the gathers
+#endif
+constexpr int RSM = SPH_FORCE_RSM;                     // records per thread kept in shared memory by the force sweep
 #ifndef SPH_FORCE_ILP
 #define SPH_FORCE_ILP 2
 #endif
@@ -84,7 +87,10 @@ constexpr int RSM = 16;                     // records per thread kept in shared
 #define SPH_FORCE_CTAS 4
 #endif
 constexpr int kForceIlp = SPH_FORCE_ILP;     // neighbours in flight per lane of the force sweep
-constexpr int kForceThreads = 128;
+#ifndef SPH_FORCE_THREADS
+#define SPH_FORCE_THREADS 128
+#endif
+constexpr int kForceThreads = SPH_FORCE_THREADS;
 constexpr int kFlatThreads = 128;
 
 struct TileLayout
