@@ -289,7 +289,7 @@ def run_ours(args):
         dom = {"key": "force", "ms": force_ms, "bytes": ALG_BYTES_FORCE,
                "kernel": "k_force_stream (pressure + viscosity + integrate + walls, hit-mask stream driven)",
                "note": "bound by L1 wavefronts of the scattered 16-byte neighbour gathers (ncu: "
-                       "l1tex__data_pipe_lsu_wavefronts 90%, DRAM 14% busy), not by HBM: DESIGN.md section 5"}
+                       "l1tex__data_pipe_lsu_wavefronts 86%, DRAM 14% busy), not by HBM: DESIGN.md section 5"}
     else:
         dom = {"key": "density", "ms": dens_ms, "bytes": ALG_BYTES_DENSITY,
                "kernel": "k_density_tiled (density + EOS + hit-mask stream sweep, packed FP32)",
