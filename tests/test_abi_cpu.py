@@ -25,6 +25,18 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, name), name
 
 
+def test_binding_argument_counts_match_the_header():
+    """ctypes does not check arity: a prototype that drifts from include/sphb200.h would
+    silently pass garbage.  Count the parameters of every declaration."""
+    header = open(os.path.join(ROOT, "include", "sphb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    protos = dict(re.findall(r"\b(sphb200_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", header))
+    for name, args, _ in binding.API:
+        params = protos[name].strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(args), "%s: header has %d parameters, binding passes %d" % (name, n, len(args))
+
+
 def test_default_params_are_the_reference_constructor_literals():
     p = S.default_params()
     assert (p.particle_count, p.grid_x, p.grid_y, p.grid_z, p.examine_count) == (32768, 32, 32, 32, 32)
