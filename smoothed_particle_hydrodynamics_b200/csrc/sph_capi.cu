@@ -409,10 +409,13 @@ int sphb200_destroy(sphb200_ctx* ctx)
       cudaEventDestroy(ctx->upload_ev[0]);
       cudaEventDestroy(ctx->upload_ev[1]);
    }
+   if (ctx->tex_posA) cudaDestroyTextureObject(ctx->tex_posA);
+   if (ctx->tex_velB) cudaDestroyTextureObject(ctx->tex_velB);
+   sph_grid_free(ctx);
    void* bufs[] = {ctx->pos4, ctx->vel4, ctx->gid, ctx->keys, ctx->keys_sorted, ctx->idx_iota, ctx->idx_sorted,
-                   ctx->cell_count, ctx->cell_start, ctx->slot_state, ctx->idx_fixed, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
+                   ctx->slot_state, ctx->idx_fixed, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
                    ctx->s_acc4, ctx->s_count, ctx->nbr_idx, ctx->nbr_dist, ctx->nbr_count, ctx->rho, ctx->acc4,
-                   ctx->voxel_id, ctx->vg_count, ctx->vg_start, ctx->vg_members, ctx->vg_keys, ctx->cub_temp,
+                   ctx->voxel_id, ctx->vg_count, ctx->vg_start, ctx->vg_members, ctx->vg_keys,
                    ctx->d_scalars, ctx->d_block_partials, ctx->stage_f, ctx->hit_rec, ctx->hit_info};
    for (void* b : bufs)
       if (b)
@@ -556,7 +559,7 @@ int sphb200_synchronize(sphb200_ctx* ctx)
       return sph_fail(nullptr, SPHB200_E_INVALID, "null context");
    SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
    SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-   return SPHB200_OK;
+   return sph_comm_check(ctx);
 }
 
 int sphb200_download(sphb200_ctx* ctx, int field, void* dst, size_t dst_bytes)
@@ -570,6 +573,13 @@ int sphb200_download(sphb200_ctx* ctx, int field, void* dst, size_t dst_bytes)
    const bool full = ctx->params.neighbor_mode == SPHB200_NEIGHBORS_FULL;
    size_t need = 0;
    const void* src = nullptr;
+   // Slab contexts index slots, not particles: FREE slots have no voxel, the voxel ids are
+   // global while the local tables cover one slab, and slot order is not particle order.
+   // The per-particle views of a slab go through sphb200_download_slab; the voxel-grid views
+   // of the reference (mVoxelIds / mGrid, sph.h:142-146) exist on single-GPU contexts only.
+   if (ctx->comm && (field == SPHB200_F_VOXEL_ID || field == SPHB200_F_VOXEL_COORD || field == SPHB200_F_GRID_START ||
+                     field == SPHB200_F_GRID_MEMBERS || field == SPHB200_F_CELL_COUNT || field == SPHB200_F_FINE_KEY))
+      return sph_fail(ctx, SPHB200_E_INVALID, "download: voxel / grid views are not defined on a slab context");
    switch (field)
    {
    case SPHB200_F_POSITION:
@@ -779,6 +789,8 @@ int sphb200_get_energies(sphb200_ctx* ctx, float* e_kin, float* e_pot)
       return sph_fail(ctx, SPHB200_E_INVALID, "null argument");
    SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
    int rc = fetch_scalars(ctx);
+   if (rc == SPHB200_OK)
+      rc = sph_comm_check(ctx);
    if (rc)
       return rc;
    *e_kin = (float)ctx->h_scalars.e_kin;
@@ -792,6 +804,8 @@ int sphb200_get_neighbor_stats(sphb200_ctx* ctx, long long* total, int* max_coun
       return sph_fail(nullptr, SPHB200_E_INVALID, "null context");
    SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
    int rc = fetch_scalars(ctx);
+   if (rc == SPHB200_OK)
+      rc = sph_comm_check(ctx);
    if (rc)
       return rc;
    if (total) *total = (long long)ctx->h_scalars.nbr_total;

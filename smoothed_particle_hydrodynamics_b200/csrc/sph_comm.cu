@@ -190,6 +190,10 @@ __global__ void __launch_bounds__(kThreads)
                  unsigned* __restrict__ counters, float4* __restrict__ pos4, float4* __restrict__ vel4,
                  uint32_t* __restrict__ gid, unsigned char* __restrict__ state)
 {
+   // a failed exchange (peer timeout, overflow) leaves stale or partial messages behind: consume
+   // nothing -- the sticky error is raised at the next host synchronisation point (sph_comm_check)
+   if (counters[1] != 0u)
+      return;
    const SlabMsgHeader hd = *reinterpret_cast<const SlabMsgHeader*>(msg_down);
    const SlabMsgHeader hu = *reinterpret_cast<const SlabMsgHeader*>(msg_up);
    unsigned c0 = min(hd.n_migrants, (unsigned)mig_cap), c1 = min(hd.n_ghosts, (unsigned)ghost_cap);
@@ -262,7 +266,15 @@ __global__ void k_slab_finalize(unsigned char* msg_down, unsigned char* msg_up, 
 
 // put mode: waits until both neighbours have published message `want` (bounded: a peer
 // that never arrives raises error 3 instead of hanging the GPU)
-__global__ void k_slab_wait(const unsigned* flags, int has_down, int has_up, unsigned want, unsigned* counters)
+__device__ __forceinline__ unsigned long long sph_globaltimer_ns()
+{
+   unsigned long long t;
+   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+   return t;
+}
+
+__global__ void k_slab_wait(const unsigned* flags, int has_down, int has_up, unsigned want, unsigned* counters,
+                            unsigned long long timeout_ns)
 {
    if (threadIdx.x != 0 || blockIdx.x != 0)
       return;
@@ -271,10 +283,10 @@ __global__ void k_slab_wait(const unsigned* flags, int has_down, int has_up, uns
    {
       if (!(d ? has_up : has_down))
          continue;
-      const long long t0 = clock64();
+      const unsigned long long t0 = sph_globaltimer_ns();
       while ((int)(f[d] - want) < 0)
       {
-         if (clock64() - t0 > 40000000000ll)     // ~20 s
+         if (sph_globaltimer_ns() - t0 > timeout_ns)
          {
             atomicMax(&counters[1], 3u);
             break;
@@ -527,8 +539,14 @@ static int slab_unpack(sphb200_ctx* ctx)
    const int par = c->put_mode ? (int)(c->exchange_no & 1u) : 0;
    if (c->put_mode)
    {
+      // wall-clock bound on the wait for a neighbour (rank skew: a peer busy with a long host-side
+      // download or a compile between steps): SPHB200_PEER_TIMEOUT_S, default 120 s
+      double timeout_s = 120.0;
+      if (const char* env = getenv("SPHB200_PEER_TIMEOUT_S"))
+         if (atof(env) > 0.0)
+            timeout_s = atof(env);
       k_slab_wait<<<1, 32, 0, ctx->stream>>>(c->flags, c->rank > 0, c->rank < c->nranks - 1, c->exchange_no,
-                                             c->counters);
+                                             c->counters, (unsigned long long)(timeout_s * 1e9));
       ctx->launches++;
    }
    int max_arrivals = 2 * (c->mig_cap + c->ghost_cap);
@@ -864,9 +882,12 @@ int sphb200_upload_slab(sphb200_ctx* ctx, int count, const float* pos_xyz, const
    ctx->n_owned = count;
    // A message built from the old state may already be published at the neighbours (put
    // mode): retire its number so that nobody consumes it.  Uploads are collective: every
-   // rank of a run uploads at the same point of its step sequence.
+   // rank of a run uploads at the same point of its step sequence (callers put a cross-rank
+   // barrier before a mid-run upload: bench.py, tests/test_gpu_multiproc.py).
+   // Two numbers, not one: parity is preserved, so the next message overwrites the receive buffer
+   // of the dead message and never the one a lagging neighbour may still be unpacking.
    if (ctx->comm->msgs_ready)
-      ctx->comm->exchange_no++;
+      ctx->comm->exchange_no += 2;
    ctx->comm->msgs_ready = false;
    SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->comm->counters, 0, sizeof(unsigned) * 2, st));
    ctx->lists_valid = false;
@@ -882,6 +903,8 @@ int sphb200_upload_slab(sphb200_ctx* ctx, int count, const float* pos_xyz, const
 int sphb200_download_slab(sphb200_ctx* ctx, int field, void* dst, size_t dst_bytes, uint32_t* global_ids, int* count)
 {
    int rc = require_slab(ctx, "download_slab");
+   if (rc == SPHB200_OK)
+      rc = sph_comm_check(ctx);
    if (rc)
       return rc;
    if (!dst || !count)
@@ -987,7 +1010,19 @@ int sphb200_slab_status(sphb200_ctx* ctx)
    int rc = require_slab(ctx, "slab_status");
    if (rc)
       return rc;
+   return sph_comm_check(ctx);
+}
+
+}  // extern "C"
+
+// The sticky error flag of the exchange, raised at every host synchronisation point of a slab
+// context (synchronize, download_slab, get_energies, get_neighbor_stats, slab_status): a step
+// whose exchange failed must not look like a good one to a caller that never polls the status.
+int sph_comm_check(sphb200_ctx* ctx)
+{
    SlabComm* c = ctx->comm;
+   if (!c)
+      return SPHB200_OK;
    SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
    SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(c->h_counters, c->counters, sizeof(unsigned) * 2, cudaMemcpyDeviceToHost,
                                        ctx->stream));
@@ -998,8 +1033,7 @@ int sphb200_slab_status(sphb200_ctx* ctx)
    if (c->h_counters[1] == 2)
       return sph_fail(ctx, SPHB200_E_CAPACITY, "slab exchange: no free particle slot left (raise particle_count)");
    if (c->h_counters[1] == 3)
-      return sph_fail(ctx, SPHB200_E_COMM, "slab exchange: a neighbour's halo message did not arrive (peer timeout)");
+      return sph_fail(ctx, SPHB200_E_COMM, "slab exchange: a neighbour's halo message did not arrive (peer timeout, "
+                                           "SPHB200_PEER_TIMEOUT_S); the state after that step is not valid");
    return SPHB200_OK;
 }
-
-}  // extern "C"

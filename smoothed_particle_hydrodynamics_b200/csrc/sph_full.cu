@@ -91,6 +91,9 @@ constexpr int kForceIlp = SPH_FORCE_ILP;     // neighbours in flight per lane of
 #define SPH_FORCE_THREADS 128
 #endif
 constexpr int kForceThreads = SPH_FORCE_THREADS;
+#ifndef SPH_FORCE_TEX
+#define SPH_FORCE_TEX 0    // neighbour gathers through the texture path: 1 = (v, fB) records, 2 = (x, fA), 3 = both (A/B)
+#endif
 constexpr int kFlatThreads = 128;
 
 struct TileLayout
@@ -679,7 +682,7 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
             if (STAGED && mask != 0u)
             {
                if (nw < WCAP)
-                  rec[(size_t)nw * 32] = make_uint2(mask, (unsigned)(c0 - delta));
+                  rec[(size_t)nw * 32] = make_uint2(mask, (unsigned)(c0 - delta) | ((unsigned)r << 28));
                nw++;
                nhits += __popc(mask);
             }
@@ -877,7 +880,7 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
             if (mask != 0u)
             {
                if (nw < WCAP)
-                  SPH_ST_ONCE(&rec[(size_t)nw * 32], make_uint2(mask, (unsigned)(c0 - delta)));
+                  SPH_ST_ONCE(&rec[(size_t)nw * 32], make_uint2(mask, (unsigned)(c0 - delta) | ((unsigned)r << 28)));
                nw++;
                nhits += __popc(mask);
             }
@@ -966,7 +969,7 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
                   const uint32_t* __restrict__ idx_sorted, const uint2* __restrict__ hit_rec,
                   const unsigned* __restrict__ hit_info, float4* __restrict__ pos4, float4* __restrict__ vel4,
                   float4* __restrict__ s_acc4, int* __restrict__ s_count, double* __restrict__ block_partials,
-                  StepScalars* scal)
+                  StepScalars* scal, cudaTextureObject_t tex_posA, cudaTextureObject_t tex_velB)
 {
    __shared__ unsigned rmask_all[RSM * kForceThreads];
    __shared__ unsigned rbase_all[RSM * kForceThreads];
@@ -1014,13 +1017,13 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
          if (w < RSM)
          {
             m = rmask[w * kForceThreads];
-            base = (int)rbase[w * kForceThreads];
+            base = (int)(rbase[w * kForceThreads] & 0x0fffffffu);
          }
          else
          {
             uint2 r2 = SPH_LD_ONCE(rec + (size_t)w * 32);
             m = r2.x;
-            base = (int)r2.y;
+            base = (int)(r2.y & 0x0fffffffu);
          }
          w++;
       }
@@ -1046,8 +1049,8 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
 #pragma unroll
       for (int q = 0; q < kForceIlp; q++)
       {
-         pj[q] = __ldg(&s_posA4[j[q]]);
-         vj[q] = __ldg(&s_velB4[j[q]]);
+         pj[q] = (SPH_FORCE_TEX & 2) ? tex1Dfetch<float4>(tex_posA, j[q]) : __ldg(&s_posA4[j[q]]);
+         vj[q] = (SPH_FORCE_TEX & 1) ? tex1Dfetch<float4>(tex_velB, j[q]) : __ldg(&s_velB4[j[q]]);
       }
       PairTerm t[kForceIlp];
 #pragma unroll
@@ -1108,6 +1111,343 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    }
    sph_block_reduce_scalars(ek, ep, cnt, cmax, cmin, block_partials, scal);
 }
+
+
+// ---- force sweep, tiled: neighbour records staged in shared memory by TMA bulk copies ----
+// k_force_stream above gathers every neighbour's two 16-byte records through L1; ncu showed
+// that kernel bound by the L1 data pipe (86 % of its wavefront rate: ~14 distinct 128-byte
+// lines per warp-wide LDG.128).  tools/ubench_gather.cu on B200: the same fetch costs 9.4
+// clocks per warp as an LDS.128 at lane-dependent slots against ~14 through L1 (the texture
+// path shares the L1 tag stage: no extra throughput).  So this kernel gives a CTA an 8x4x2
+// block of fine cells, copies the block's particles plus the one-cell halo -- 24 x-contiguous
+// row segments of (x,y,z,fA) and of (vx,vy,vz,fB), 32 bytes per particle -- into shared
+// memory with one cp.async.bulk per row and array (no registers, no transposition; an
+// mbarrier counts the bytes), and every lane walks the set bits of its particle's hit-mask
+// records against shared memory.  A record names its x-run (bits 28-31 of the base), which
+// gives the halo row and with it the displacement global sorted index -> staged slot.
+// Blocks whose halo does not fit (dense clumps) walk the same records against global
+// memory; particles without a stream scan their 27 cells as in k_force_stream.
+#ifndef SPH_FTX
+#define SPH_FTX 8
+#endif
+#ifndef SPH_FTY
+#define SPH_FTY 4
+#endif
+#ifndef SPH_FTZ
+#define SPH_FTZ 2
+#endif
+#ifndef SPH_FCAP
+#define SPH_FCAP 2944
+#endif
+#ifndef SPH_FTHREADS
+#define SPH_FTHREADS 320
+#endif
+#ifndef SPH_FCTAS
+#define SPH_FCTAS 2
+#endif
+constexpr int FTX = SPH_FTX, FTY = SPH_FTY, FTZ = SPH_FTZ;
+constexpr int FHROWS = (FTY + 2) * (FTZ + 2);   // halo rows of a force tile (<= 32: one warp lays them out)
+constexpr int FTROWS = FTY * FTZ;
+constexpr int kFCap = SPH_FCAP;                 // staged particles per tile, 32 bytes each
+constexpr int kFThreads = SPH_FTHREADS;
+static_assert(FHROWS <= 32, "one warp computes the layout of a force tile");
+constexpr unsigned kRunShift = 28;              // record base: sorted index | x-run number << 28
+constexpr unsigned kBaseMask = (1u << kRunShift) - 1u;
+
+struct ForceLayout
+{
+   int row_delta[FHROWS];     // staged slot = sorted index + row_delta (0 when the tile is not staged)
+   int tgt_off[FTROWS + 1];   // prefix of the target counts per target row
+   int tgt_k0[FTROWS];        // sorted index of the first target of the row
+   int ntargets, staged;
+   unsigned long long mbar;
+};
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                "r"(bytes)
+                : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+   const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+   asm volatile("{\n"
+                ".reg .pred p;\n"
+                "WAIT_%=:\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                "@p bra DONE_%=;\n"
+                "bra WAIT_%=;\n"
+                "DONE_%=:\n"
+                "}" ::"r"(a),
+                "r"(parity)
+                : "memory");
+}
+
+// 1-D TMA bulk copy global -> shared; completion is counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src, unsigned bytes, unsigned long long* bar)
+{
+   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst_smem)),
+                "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                : "memory");
+}
+
+// the hit walk of one target against `A` / `B` (shared memory when STAGED, else the global
+// arrays with a zero displacement).  Same visiting order and arithmetic as k_force_stream.
+template <bool UNIT_SCALE, bool STAGED>
+__device__ __forceinline__ void force_walk(const DevParams& P, const ForceI& I, const ForceLayout& L, int hrb,
+                                           int self_slot, const float4* A, const float4* B, const uint2* rec, int nw,
+                                           int nhits, Vec3& pg, Vec3& vt, int& count)
+{
+   int w = 0;
+   unsigned m = 0;
+   int base = 0;
+   // the next record is fetched one ahead of its use (its latency hides behind ~3 neighbours)
+   uint2 nxt = nw > 0 ? SPH_LD_ONCE(rec) : make_uint2(0u, 0u);
+   auto next_hit = [&]() -> int {
+      if (m == 0u)
+      {
+         m = nxt.x;
+         const unsigned run = nxt.y >> kRunShift;
+         base = (int)(nxt.y & kBaseMask);
+         if (STAGED)
+         {
+            const unsigned rz = (run * 11u) >> 5;   // run / 3, run < 9
+            base += L.row_delta[hrb + (int)(rz * (FTY + 2) + (run - 3u * rz))];
+         }
+         w++;
+         if (w < nw)
+            nxt = SPH_LD_ONCE(rec + (size_t)w * 32);
+      }
+      const int lead = __clz((int)m);
+      m &= ~(0x80000000u >> lead);
+      return base + lead;
+   };
+   const int nmax = __reduce_max_sync(0xffffffffu, nhits);
+#pragma unroll 1
+   for (int it = 0; it < nmax; it += kForceIlp)
+   {
+      int j[kForceIlp];
+      float4 pj[kForceIlp], vj[kForceIlp];
+#pragma unroll
+      for (int q = 0; q < kForceIlp; q++)
+      {
+         j[q] = self_slot;
+         if (it + q < nhits)
+            j[q] = next_hit();
+      }
+#pragma unroll
+      for (int q = 0; q < kForceIlp; q++)
+      {
+         pj[q] = STAGED ? A[j[q]] : __ldg(&A[j[q]]);
+         vj[q] = STAGED ? B[j[q]] : __ldg(&B[j[q]]);
+      }
+      PairTerm t[kForceIlp];
+#pragma unroll
+      for (int q = 0; q < kForceIlp; q++)
+         t[q] = force_term<UNIT_SCALE>(P, I, pj[q], vj[q], j[q] != self_slot);
+#pragma unroll
+      for (int q = 0; q < kForceIlp; q++)
+         force_accumulate(I, t[q], pg, vt, count);
+   }
+}
+
+template <bool UNIT_SCALE>
+__global__ void __launch_bounds__(kFThreads, SPH_FCTAS)
+   k_force_tiled(DevParams P, const float4* __restrict__ s_pos4, const float4* __restrict__ s_posA4,
+                 const float4* __restrict__ s_velB4, const float* __restrict__ s_rho,
+                 const uint32_t* __restrict__ keys_sorted, const uint32_t* __restrict__ cell_start,
+                 const uint32_t* __restrict__ idx_sorted, const uint2* __restrict__ hit_rec,
+                 const unsigned* __restrict__ hit_info, float4* __restrict__ pos4, float4* __restrict__ vel4,
+                 float4* __restrict__ s_acc4, int* __restrict__ s_count, double* __restrict__ block_partials,
+                 StepScalars* scal)
+{
+   extern __shared__ __align__(128) unsigned char smem_raw[];
+   float4* sA = reinterpret_cast<float4*>(smem_raw);
+   float4* sB = sA + kFCap;
+   __shared__ ForceLayout L;
+   const int X0 = blockIdx.x * FTX, Y0 = blockIdx.y * FTY, Z0 = blockIdx.z * FTZ;
+   const int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+   const int lane = threadIdx.x & 31;
+   if (threadIdx.x < 32)
+   {
+      if (lane == 0)
+         mbar_init(&L.mbar, 1);
+      // one lane per halo row: its segment [g0, g1) of the sorted arrays and, for the rows of
+      // the block itself, the targets [t0, t1)
+      const int hy = lane % (FTY + 2), hz = lane / (FTY + 2);
+      const int y = Y0 - 1 + hy, z = Z0 - 1 + hz;
+      int g0 = 0, g1 = 0, t0 = 0, t1 = 0;
+      if (lane < FHROWS && y >= 0 && y < P.fy && z >= 0 && z < P.fz)
+      {
+         const uint32_t* row = cell_start + (size_t)(z * P.fy + y) * P.fx;
+         g0 = (int)__ldg(row + max(X0 - 1, 0));
+         g1 = (int)__ldg(row + min(X0 + FTX + 1, P.fx));
+         if (hy >= 1 && hy <= FTY && hz >= 1 && hz <= FTZ)
+         {
+            t0 = (int)__ldg(row + X0);
+            t1 = (int)__ldg(row + min(X0 + FTX, P.fx));
+         }
+      }
+      const int len = g1 - g0, tc = t1 - t0;
+      int incl = len, tincl = tc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+         const int up = __shfl_up_sync(0xffffffffu, incl, o), tup = __shfl_up_sync(0xffffffffu, tincl, o);
+         if (lane >= o)
+         {
+            incl += up;
+            tincl += tup;
+         }
+      }
+      const int total = __shfl_sync(0xffffffffu, incl, 31), ntargets = __shfl_sync(0xffffffffu, tincl, 31);
+      const bool staged = total <= kFCap;
+      if (lane < FHROWS)
+      {
+         L.row_delta[lane] = staged ? (incl - len) - g0 : 0;
+         if (hy >= 1 && hy <= FTY && hz >= 1 && hz <= FTZ)
+         {
+            const int r = (hz - 1) * FTY + (hy - 1);   // target rows ascend with the halo row number
+            L.tgt_off[r] = tincl - tc;
+            L.tgt_k0[r] = t0;
+         }
+      }
+      if (lane == 0)
+      {
+         L.tgt_off[FTROWS] = ntargets;
+         L.ntargets = ntargets;
+         L.staged = staged ? 1 : 0;
+      }
+      if (staged && ntargets > 0)
+      {
+         __syncwarp();
+         if (lane == 0)
+            mbar_expect_tx(&L.mbar, (unsigned)total * 32u);
+         __syncwarp();
+         if (len > 0)
+         {
+            bulk_g2s(sA + (incl - len), s_posA4 + g0, (unsigned)len * 16u, &L.mbar);
+            bulk_g2s(sB + (incl - len), s_velB4 + g0, (unsigned)len * 16u, &L.mbar);
+         }
+      }
+   }
+   __syncthreads();
+   const int ntargets = L.ntargets;
+   if (ntargets == 0)
+   {
+      if (threadIdx.x == 0)
+      {
+         block_partials[2 * bid] = 0.0;
+         block_partials[2 * bid + 1] = 0.0;
+      }
+      return;
+   }
+   const bool staged = L.staged != 0;
+   double ek = 0.0, ep = 0.0;
+   unsigned long long cnt = 0;
+   int cmax = -1, cmin = 0x7fffffff;
+   if (staged)
+      mbar_wait(&L.mbar, 0);
+   const int live = sph_live_count(P);
+   // whole warps walk the targets so that the warp-wide votes below see every lane
+   for (int tb = (int)(threadIdx.x & ~31u); tb < ntargets; tb += kFThreads)
+   {
+      const int tnum = tb + lane;
+      const bool valid = tnum < ntargets;
+      const int tn = valid ? tnum : ntargets - 1;
+      int r = 0;
+#pragma unroll
+      for (int i = 1; i < FTROWS; i++)
+         r += (tn >= L.tgt_off[i]) ? 1 : 0;
+      const int k = L.tgt_k0[r] + (tn - L.tgt_off[r]);
+      const int rz = r / FTY;
+      const int hr0 = (rz + 1) * (FTY + 2) + (r - rz * FTY) + 1;
+      bool active = valid;
+      if (P.slab && active)
+      {
+         // ghost-layer particles only lend their density / velocity to owned neighbours;
+         // the rank that owns them integrates them
+         const int cz = Z0 + rz;
+         active = cz >= 2 * P.ghost_lo && cz < P.fz - 2 * P.ghost_hi;
+      }
+      const int self_slot = k + L.row_delta[hr0];
+      const unsigned info = active ? SPH_LD_ONCE(&hit_info[k]) : 0u;
+      const float4 pi = staged ? sA[self_slot] : s_posA4[k];
+      const float4 vi = staged ? sB[self_slot] : s_velB4[k];
+      const float rho_i = SPH_LD_ONCE(&s_rho[k]);
+      const bool scan = (info & 0xffu) == kNoStream;
+      const int nw = scan ? 0 : (int)(info & 0xffu);
+      const int nhits = scan ? 0 : (int)(info >> 8);
+      const uint2* rec = hit_rec + stream_base(k);
+      const ForceI I = make_force_i(P, pi, vi, rho_i);
+      Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
+      int count = 0;
+      if (staged)
+         force_walk<UNIT_SCALE, true>(P, I, L, hr0 - (FTY + 2) - 1, self_slot, sA, sB, rec, nw, nhits, pg, vt, count);
+      else
+         force_walk<UNIT_SCALE, false>(P, I, L, 0, k, s_posA4, s_velB4, rec, nw, nhits, pg, vt, count);
+      if (scan && active)
+      {
+         int b[9], e[9];
+         global_runs(P, keys_sorted[k], cell_start, b, e);
+#pragma unroll 1
+         for (int q = 0; q < 9; q++)
+            for (int j = b[q]; j < e[q]; j++)
+               count += force_candidate<UNIT_SCALE>(P, I, __ldg(&s_posA4[j]), __ldg(&s_velB4[j]), j != k, pg, vt);
+      }
+      float4 new_pos = make_float4(0.0f, 0.0f, 0.0f, 0.0f), new_vel = new_pos;
+      if (active)
+      {
+         double e_k, e_p;
+         force_store(P, k, I, vt, pg, count, s_pos4, idx_sorted, pos4, vel4, s_acc4, s_count, e_k, e_p, new_pos,
+                     new_vel);
+         ek += e_k;
+         ep += e_p;
+         cnt += (unsigned long long)count;
+         cmax = max(cmax, count);
+         cmin = min(cmin, count);
+      }
+      if (P.slab)
+      {
+         // see k_force_stream: the new position decides whether the particle goes into the
+         // next halo message or migrates
+         bool owned = active;
+         uint32_t o = 0;
+         if (valid && k < live)
+         {
+            o = idx_sorted[k];
+            if (!active)
+            {
+               s_count[k] = 0;
+               s_acc4[k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            }
+            if (!active && P.slot_state[o] == SLOT_OWNED)
+            {
+               new_pos = pos4[o];
+               new_vel = vel4[o];
+               owned = true;
+            }
+         }
+         if (owned)
+            new_vel.w = __uint_as_float(P.slot_gid[o]);
+         const unsigned char st = sph_slab_emit(P, owned, new_pos, new_vel);
+         if (owned && st != SLOT_OWNED)
+            P.slot_state[o] = st;
+      }
+   }
+   sph_block_reduce_scalars(ek, ep, cnt, cmax, cmin, block_partials, scal, bid);
+}
+
+size_t force_smem() { return 32 * (size_t)kFCap; }
 
 // velocities into the force records after a density sweep that ran with defer_velocity
 __global__ void __launch_bounds__(kFlatThreads)
@@ -1190,17 +1530,39 @@ int sph_full_configure(sphb200_ctx* ctx)
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem()));
    SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_tiled<false, false>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem()));
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_force_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)force_smem()));
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_force_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)force_smem()));
+   if (ctx->capacity >= (1 << 28))
+      return sph_fail(ctx, SPHB200_E_INVALID, "FULL mode: at most 2^28 - 1 particle slots per GPU (hit-mask record format)");
    // hit-mask stream: WCAP records per particle, interleaved per 32 sorted particles
    size_t groups = ((size_t)ctx->capacity + 31) / 32;
    SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->hit_rec, sizeof(uint2) * (groups ? groups : 1) * WCAP * 32));
    SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->hit_info, sizeof(unsigned) * (size_t)(ctx->capacity + 1)));
+   if (SPH_FORCE_TEX && ctx->capacity > 0)
+   {
+      cudaResourceDesc rd = {};
+      rd.resType = cudaResourceTypeLinear;
+      rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+      rd.res.linear.sizeInBytes = sizeof(float4) * (size_t)ctx->capacity;
+      cudaTextureDesc td = {};
+      td.readMode = cudaReadModeElementType;
+      rd.res.linear.devPtr = ctx->s_posA4;
+      SPH_CUDA_CHECK(ctx, cudaCreateTextureObject(&ctx->tex_posA, &rd, &td, nullptr));
+      rd.res.linear.devPtr = ctx->s_velB4;
+      SPH_CUDA_CHECK(ctx, cudaCreateTextureObject(&ctx->tex_velB, &rd, &td, nullptr));
+   }
    return SPHB200_OK;
 }
 
+// CTAs of the largest tiled launch (sizes the per-block partials of the energy reduction)
 int sph_full_tile_count(const sphb200_ctx* ctx)
 {
    int fx = 2 * ctx->params.grid_x, fy = 2 * ctx->params.grid_y, fz = 2 * ctx->params.grid_z;
-   return ((fx + TBX - 1) / TBX) * ((fy + TBY - 1) / TBY) * ((fz + TBZ - 1) / TBZ);
+   int dens = ((fx + TBX - 1) / TBX) * ((fy + TBY - 1) / TBY) * ((fz + TBZ - 1) / TBZ);
+   int force = ((fx + FTX - 1) / FTX) * ((fy + FTY - 1) / FTY) * ((fz + FTZ - 1) / FTZ);
+   return dens > force ? dens : force;
 }
 
 int sph_step_full(sphb200_ctx* ctx)
@@ -1254,17 +1616,39 @@ int sph_step_full(sphb200_ctx* ctx)
       ctx->launches++;
    }
    if (timed) cudaEventRecord(ctx->ev[4], st);
-   const int blocks = (n + kForceThreads - 1) / kForceThreads;
-   if (P.scale == 1.0f)
-      k_force_stream<true><<<blocks, kForceThreads, 0, st>>>(
-         P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_order,
-         ctx->hit_rec, ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
-         ctx->d_scalars);
+   // force sweep: tiled + staged in shared memory (default), or the flat L1-gather kernel
+   // (kernel_variant 1 = everything untiled, 2 = tiled density + flat force, for A/B and as
+   // the reference of the tiled kernels' parity tests)
+   int blocks;
+   if (ctx->params.kernel_variant == 0)
+   {
+      dim3 ft((P.fx + FTX - 1) / FTX, (P.fy + FTY - 1) / FTY, (P.fz + FTZ - 1) / FTZ);
+      blocks = (int)(ft.x * ft.y * ft.z);
+      if (P.scale == 1.0f)
+         k_force_tiled<true><<<ft, kFThreads, force_smem(), st>>>(
+            P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_order,
+            ctx->hit_rec, ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
+            ctx->d_scalars);
+      else
+         k_force_tiled<false><<<ft, kFThreads, force_smem(), st>>>(
+            P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_order,
+            ctx->hit_rec, ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
+            ctx->d_scalars);
+   }
    else
-      k_force_stream<false><<<blocks, kForceThreads, 0, st>>>(
-         P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_order,
-         ctx->hit_rec, ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
-         ctx->d_scalars);
+   {
+      blocks = (n + kForceThreads - 1) / kForceThreads;
+      if (P.scale == 1.0f)
+         k_force_stream<true><<<blocks, kForceThreads, 0, st>>>(
+            P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_order,
+            ctx->hit_rec, ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
+            ctx->d_scalars, ctx->tex_posA, ctx->tex_velB);
+      else
+         k_force_stream<false><<<blocks, kForceThreads, 0, st>>>(
+            P, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->keys_sorted, ctx->cell_start, ctx->idx_order,
+            ctx->hit_rec, ctx->hit_info, ctx->pos4, ctx->vel4, ctx->s_acc4, ctx->s_count, ctx->d_block_partials,
+            ctx->d_scalars, ctx->tex_posA, ctx->tex_velB);
+   }
    ctx->launches += 2;
    SPH_CUDA_CHECK(ctx, cudaGetLastError());
    if (timed) cudaEventRecord(ctx->ev[5], st);   // integrate is fused into the force sweep

@@ -123,6 +123,7 @@ struct sphb200_ctx
    int* s_count;          // sorted neighbour count
    uint2* hit_rec;        // FULL mode hit-mask stream {mask, smem byte offset}, see sph_full.cu
    unsigned* hit_info;    // per sorted particle: records | hits << 8, or 0xff = scan
+   cudaTextureObject_t tex_posA, tex_velB;   // linear float4 views of s_posA4 / s_velB4 (force-sweep A/B: TEX path)
 
    // SAMPLED mode / on-demand lists, original order
    uint32_t* nbr_idx;     // N * E
@@ -194,6 +195,7 @@ int sph_comm_exchange(sphb200_ctx* ctx);
 int sph_comm_begin_step(sphb200_ctx* ctx);
 int sph_comm_end_step(sphb200_ctx* ctx);
 void sph_comm_free(sphb200_ctx* ctx);
+int sph_comm_check(sphb200_ctx* ctx);   // sticky exchange error -> status code (no-op without a slab)
 void sph_comm_dev_params(const sphb200_ctx* ctx, DevParams& P);
 int sph_grid_alloc(sphb200_ctx* ctx);
 void sph_grid_free(sphb200_ctx* ctx);

@@ -299,8 +299,11 @@ __device__ __forceinline__ unsigned char sph_slab_emit(const DevParams& P, bool 
 // partial per block (deterministic two-stage reduction; finished by
 // sph_finish_scalars).  blockDim.x must be a multiple of 32, <= 1024.
 __device__ __forceinline__ void sph_block_reduce_scalars(double ek, double ep, unsigned long long cnt, int cmax,
-                                                         int cmin, double* block_partials, StepScalars* scal)
+                                                         int cmin, double* block_partials, StepScalars* scal,
+                                                         int partial_index = -1)
 {
+   if (partial_index < 0)
+      partial_index = (int)blockIdx.x;
    __shared__ double s_ek[32], s_ep[32];
    __shared__ unsigned long long s_cnt[32];
    __shared__ int s_max[32], s_min[32];
@@ -342,8 +345,8 @@ __device__ __forceinline__ void sph_block_reduce_scalars(double ek, double ep, u
       }
       if (lane == 0)
       {
-         block_partials[2 * blockIdx.x] = ek;
-         block_partials[2 * blockIdx.x + 1] = ep;
+         block_partials[2 * partial_index] = ek;
+         block_partials[2 * partial_index + 1] = ep;
          atomicAdd(&scal->nbr_total, cnt);      // integer: order independent
          atomicMax(&scal->nbr_max, cmax);
          atomicMin(&scal->nbr_min, cmin);
