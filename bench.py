@@ -169,7 +169,7 @@ def run_ours(args):
     sp = scenes.scene_params(nu=NU)
     common = dict(examine_count=96, neighbor_mode=S.FULL, use_uniform_gravity=1, use_wall_collision=1,
                   rho0=sp["rho0"], stiffness=sp["stiffness"], viscosity=sp["viscosity"], central_mass=0.0,
-                  gravity=sp["gravity"], time_step=sp["time_step"])
+                  gravity=sp["gravity"], time_step=sp["time_step"], kernel_variant=args.kernel_variant)
     strong = args.scaling == "strong"
     force_slab = world == 1 and args.force_slab
     if world == 1 and not force_slab:
@@ -460,6 +460,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--nu", type=float, default=40.0,
                     help="lattice spacing for this many neighbours in the continuum limit (config 5 sweep: 30/60/120)")
+    ap.add_argument("--kernel-variant", type=int, default=0,
+                    help="A/B: 0 = tiled density + flat force sweep (default), 3 = force sweep tiled in shared memory, 1 = untiled")
     ap.add_argument("--force-slab", action="store_true", help="N=1: run the slab code path as a single slab")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="N>1: 16.7M particles per GPU (weak, default) or 16.7M in total (strong)")

@@ -72,8 +72,9 @@ typedef struct SphParams
    float softening;           /* [rt] sph.cpp:86;  <0 => h*scale               */
    float gravity[3];          /* [rt] sph.cpp:76                               */
    /* engine knobs (no reference counterpart) */
-   int kernel_variant;        /* FULL mode: 0 = auto (tiled sweeps), 1 = untiled,
-                                 2 = tiled density + flat force sweep (A/B)   */
+   int kernel_variant;        /* FULL mode: 0 = auto (tiled density sweep + flat
+                                 force sweep), 1 = untiled, 3 = force sweep
+                                 tiled in shared memory too (A/B)             */
    int enable_timers;         /* [rt] CUDA-event phase timers (updateElapsed)  */
    int reserved[6];
 } SphParams;

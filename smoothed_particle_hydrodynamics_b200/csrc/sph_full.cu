@@ -92,7 +92,9 @@ constexpr int kForceIlp = SPH_FORCE_ILP;     // neighbours in flight per lane of
 #endif
 constexpr int kForceThreads = SPH_FORCE_THREADS;
 #ifndef SPH_FORCE_TEX
-#define SPH_FORCE_TEX 0    // neighbour gathers through the texture path: 1 = (v, fB) records, 2 = (x, fA), 3 = both (A/B)
+#define SPH_FORCE_TEX 1    // neighbour gathers through the texture path: 1 = (v, fB) records, 2 = (x, fA), 3 = both
+                           // (0: 2.41 ms, 1: 2.31, 2: 2.38, 3: 2.42 at 16.7M particles; the TEX path shares the L1 tag
+                           // stage with LDG -- tools/ubench_gather.cu -- but copes better with scattered lanes)
 #endif
 constexpr int kFlatThreads = 128;
 
@@ -1616,11 +1618,11 @@ int sph_step_full(sphb200_ctx* ctx)
       ctx->launches++;
    }
    if (timed) cudaEventRecord(ctx->ev[4], st);
-   // force sweep: tiled + staged in shared memory (default), or the flat L1-gather kernel
-   // (kernel_variant 1 = everything untiled, 2 = tiled density + flat force, for A/B and as
-   // the reference of the tiled kernels' parity tests)
+   // force sweep: the flat L1-gather kernel (default), or -- kernel_variant 3 -- the tiled kernel
+   // that stages the neighbour records in shared memory by TMA bulk copies (measured slower on
+   // B200, profiles/r02_history.md: 5.09 vs 2.41 ms at 16.7M particles; kept for A/B)
    int blocks;
-   if (ctx->params.kernel_variant == 0)
+   if (ctx->params.kernel_variant == 3)
    {
       dim3 ft((P.fx + FTX - 1) / FTX, (P.fy + FTY - 1) / FTY, (P.fz + FTZ - 1) / FTZ);
       blocks = (int)(ft.x * ft.y * ft.z);

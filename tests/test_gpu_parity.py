@@ -191,7 +191,7 @@ def _compare_full_step(sph, o, tag, check_lists=True, conditioned=False):
     return mask
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["tiled", "flat"])
+@pytest.mark.parametrize("variant", [0, 1, 3], ids=["tiled", "flat", "tiled_force"])
 def test_full_dambreak_vs_reference_golden(golden_full, variant):
     g = golden_full
     cfg = scenes.CONFIGS["dambreak_16k"]
@@ -214,7 +214,7 @@ def test_full_dambreak_vs_reference_golden(golden_full, variant):
     sph.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["tiled", "flat"])
+@pytest.mark.parametrize("variant", [0, 1, 3], ids=["tiled", "flat", "tiled_force"])
 @pytest.mark.parametrize("name,sigma", [("dambreak_16k", 0.0), ("dambreak_16k", 3.0), ("dambreak_128k", 1.0)])
 def test_full_steps_vs_oracle(name, sigma, variant):
     cfg = scenes.CONFIGS[name]
@@ -236,7 +236,7 @@ def test_full_steps_vs_oracle(name, sigma, variant):
     sph.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1], ids=["tiled", "flat"])
+@pytest.mark.parametrize("variant", [0, 1, 3], ids=["tiled", "flat", "tiled_force"])
 def test_full_clumps_and_edges_vs_oracle(variant):
     """Dense clumps (exercise tile sub-division and the global fallback), an
     empty region, particles outside the box, coincident particles, one NaN."""
