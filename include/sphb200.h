@@ -149,6 +149,12 @@ int sphb200_step_host(sphb200_ctx* ctx, float* pos_xyz, float* vel_xyz, const fl
 /* FULL mode only: materialise mNeighbors / mNeighborDistancesScaled for the
  * LAST step's pre-step positions (the hot kernels never store lists) */
 int sphb200_build_neighbor_lists(sphb200_ctx* ctx);
+/* The same lists rebuilt from what the HOT PATH itself recorded: the hit-mask stream the
+ * density sweep of the last step wrote and the force sweep walked (exact test of
+ * sph.cpp:633-653 applied to the survivors, in the sweep's visiting order).  A parity
+ * instrument: equal to the independent scan above <=> the stream-driven force sweep saw
+ * exactly the reference's neighbour sets.  FULL mode, after a step. */
+int sphb200_build_neighbor_lists_visited(sphb200_ctx* ctx);
 
 /* ---- per-step scalars ------------------------------------------------------- */
 /* mKineticEnergyTotal / mPotentialEnergyTotal of the last step (sph.cpp:1004-1007) */

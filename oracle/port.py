@@ -159,6 +159,12 @@ class OracleSPH:
                                   int(use_gravity), int(use_walls), C.byref(ek), C.byref(ep))
         self.ekin, self.epot = ek.value, ep.value
 
+    def step_density_only(self, mode=SAMPLED):
+        """The first three phases of step(): binning, neighbour search, density (large-N checks)."""
+        self.voxelize()
+        self.find(mode)
+        self.compute_density()
+
     def step(self, mode=SAMPLED, use_gravity=False, use_walls=False):
         """SPH::step() order (sph.cpp:190-304)."""
         self.voxelize()

@@ -82,6 +82,7 @@ API = [
     ("sphb200_synchronize", [_VP], C.c_int),
     ("sphb200_step_host", [_VP, _VP, _VP, _VP], C.c_int),
     ("sphb200_build_neighbor_lists", [_VP], C.c_int),
+    ("sphb200_build_neighbor_lists_visited", [_VP], C.c_int),
     ("sphb200_get_energies", [_VP, C.POINTER(C.c_float), C.POINTER(C.c_float)], C.c_int),
     ("sphb200_get_neighbor_stats", [_VP, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
     ("sphb200_get_timings", [_VP, C.POINTER(C.c_float)], C.c_int),
@@ -298,8 +299,12 @@ class SPH:
     def synchronize(self):
         self._check(self._lib.sphb200_synchronize(self._h))
 
-    def build_neighbor_lists(self):
-        self._check(self._lib.sphb200_build_neighbor_lists(self._h))
+    def build_neighbor_lists(self, visited=False):
+        """visited=True: from the hit-mask stream the force sweep of the last step walked."""
+        if visited:
+            self._check(self._lib.sphb200_build_neighbor_lists_visited(self._h))
+        else:
+            self._check(self._lib.sphb200_build_neighbor_lists(self._h))
 
     def energies(self):
         ek, ep = C.c_float(), C.c_float()

@@ -255,6 +255,7 @@ static int step_graph(sphb200_ctx* ctx, int n_steps)
    const bool full = ctx->params.neighbor_mode == SPHB200_NEIGHBORS_FULL;
    ctx->lists_valid = !full;
    ctx->snapshot_valid = full;
+   ctx->stream_valid = full && ctx->params.kernel_variant != 1;
    ctx->unsorted_valid = false;
    ctx->voxel_ids_valid = true;
    ctx->idx_order = ctx->idx_sorted;
@@ -523,6 +524,7 @@ int sphb200_upload_state(sphb200_ctx* ctx, const float* pos_xyz, const float* ve
    sph_graph_invalidate(ctx);
    ctx->lists_valid = false;
    ctx->snapshot_valid = false;
+   ctx->stream_valid = false;
    ctx->voxel_ids_valid = false;
    ctx->unsorted_valid = false;
    ctx->stepped = false;
@@ -781,6 +783,19 @@ int sphb200_build_neighbor_lists(sphb200_ctx* ctx)
    if (rc)
       return rc;
    return sph_full_build_lists(ctx);
+}
+
+int sphb200_build_neighbor_lists_visited(sphb200_ctx* ctx)
+{
+   if (!ctx)
+      return sph_fail(nullptr, SPHB200_E_INVALID, "null context");
+   if (ctx->params.neighbor_mode != SPHB200_NEIGHBORS_FULL)
+      return sph_fail(ctx, SPHB200_E_INVALID, "build_neighbor_lists_visited: FULL neighbour mode only");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   int rc = alloc_lists(ctx);
+   if (rc)
+      return rc;
+   return sph_full_build_lists(ctx, true);
 }
 
 int sphb200_get_energies(sphb200_ctx* ctx, float* e_kin, float* e_pot)

@@ -892,6 +892,7 @@ int sphb200_upload_slab(sphb200_ctx* ctx, int count, const float* pos_xyz, const
    SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->comm->counters, 0, sizeof(unsigned) * 2, st));
    ctx->lists_valid = false;
    ctx->snapshot_valid = false;
+   ctx->stream_valid = false;
    ctx->voxel_ids_valid = false;
    ctx->unsorted_valid = false;
    ctx->stepped = false;

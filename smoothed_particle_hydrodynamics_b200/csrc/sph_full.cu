@@ -1503,6 +1503,68 @@ __global__ void __launch_bounds__(kFlatThreads)
       atomicMax(&scal->overflow, count);
 }
 
+// The same lists from the hit-mask stream of the last step: every record is walked exactly as
+// the force sweep walks it (MSB first, exact test on the survivors), so the result IS the
+// sequence of neighbours the hot path visited.  Particles without a stream scan, as there.
+__global__ void __launch_bounds__(kFlatThreads)
+   k_lists_from_stream(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ keys_sorted,
+                       const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ idx_sorted,
+                       const uint2* __restrict__ hit_rec, const unsigned* __restrict__ hit_info,
+                       uint32_t* __restrict__ nbr_idx, float* __restrict__ nbr_dist, int* __restrict__ nbr_count,
+                       StepScalars* scal)
+{
+   int k = blockIdx.x * blockDim.x + threadIdx.x;
+   if (k >= P.n)
+      return;
+   const float4 pi = s_pos4[k];
+   const int E = P.examine;
+   const uint32_t o = idx_sorted[k];
+   int count = 0;
+   auto visit = [&](int j) {
+      float4 pj = __ldg(&s_pos4[j]);
+      float d2 = sph_dist2_exact(pi.x, pi.y, pi.z, pj.x, pj.y, pj.z);
+      if (d2 < P.h2 && j != k)
+      {
+         if (count < E)
+         {
+            nbr_idx[(size_t)o * E + count] = idx_sorted[j];
+            nbr_dist[(size_t)o * E + count] = __fmul_rn(__fsqrt_rn(d2), P.scale);
+         }
+         count++;
+      }
+   };
+   const unsigned info = hit_info[k];
+   if ((info & 0xffu) == kNoStream)
+   {
+      int b[9], e[9];
+      global_runs(P, keys_sorted[k], cell_start, b, e);
+#pragma unroll 1
+      for (int r = 0; r < 9; r++)
+         for (int j = b[r]; j < e[r]; j++)
+            visit(j);
+   }
+   else
+   {
+      const uint2* rec = hit_rec + stream_base(k);
+      const int nw = (int)(info & 0xffu);
+      for (int w = 0; w < nw; w++)
+      {
+         uint2 r2 = rec[(size_t)w * 32];
+         unsigned m = r2.x;
+         const int base = (int)(r2.y & 0x0fffffffu);
+         while (m)
+         {
+            int lead = __clz((int)m);
+            m &= ~(0x80000000u >> lead);
+            visit(base + lead);
+         }
+      }
+   }
+   nbr_count[o] = count;
+   if (count > E)
+      atomicMax(&scal->overflow, count);
+}
+
 // sorted per-particle outputs back to particle-index order (download only)
 __global__ void __launch_bounds__(kFlatThreads)
    k_unsort(DevParams P, const uint32_t* __restrict__ idx_sorted, const float* __restrict__ s_rho,
@@ -1666,6 +1728,7 @@ int sph_step_full(sphb200_ctx* ctx)
    }
    ctx->lists_valid = false;
    ctx->snapshot_valid = true;
+   ctx->stream_valid = tiled;
    ctx->unsorted_valid = false;
    return SPHB200_OK;
 }
@@ -1683,13 +1746,25 @@ int sph_full_unsort(sphb200_ctx* ctx)
    return SPHB200_OK;
 }
 
-int sph_full_build_lists(sphb200_ctx* ctx)
+int sph_full_build_lists(sphb200_ctx* ctx, bool from_stream)
 {
    if (!ctx->snapshot_valid)
       return sph_fail(ctx, SPHB200_E_INVALID, "build_neighbor_lists: no FULL-mode step snapshot (step first)");
+   if (from_stream && !ctx->stream_valid)
+      return sph_fail(ctx, SPHB200_E_INVALID, "build_neighbor_lists_visited: the last step left no hit-mask stream");
+   if (from_stream && ctx->comm)
+      return sph_fail(ctx, SPHB200_E_INVALID, "build_neighbor_lists_visited: single-GPU contexts only");
    DevParams P = sph_dev_params(ctx);
    const int n = ctx->n_local;
-   if (n > 0)
+   if (n > 0 && from_stream)
+   {
+      k_lists_from_stream<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, ctx->stream>>>(
+         P, ctx->s_pos4, ctx->keys_sorted, ctx->cell_start, ctx->idx_order, ctx->hit_rec, ctx->hit_info, ctx->nbr_idx,
+         ctx->nbr_dist, ctx->nbr_count, ctx->d_scalars);
+      ctx->launches++;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   }
+   else if (n > 0)
    {
       k_build_lists<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, ctx->stream>>>(
          P, ctx->s_pos4, ctx->keys_sorted, ctx->cell_start, ctx->idx_order, ctx->nbr_idx, ctx->nbr_dist,

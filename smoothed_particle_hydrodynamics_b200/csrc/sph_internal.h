@@ -136,6 +136,7 @@ struct sphb200_ctx
    bool lists_valid;
    bool voxel_ids_valid;  // voxel_id[] matches the last binning / current upload
    bool snapshot_valid;   // sorted snapshot + cell table of the last FULL step present
+   bool stream_valid;     // hit-mask stream of the last FULL step present (tiled density sweep)
    uint32_t *vg_count, *vg_start, *vg_members, *vg_keys;   // lazily allocated voxel-grid views
 
    void* cub_temp;
@@ -185,7 +186,7 @@ int sph_grid_setup(sphb200_ctx* ctx);
 int sph_step_sampled(sphb200_ctx* ctx);
 // sph_full.cu
 int sph_step_full(sphb200_ctx* ctx);
-int sph_full_build_lists(sphb200_ctx* ctx);
+int sph_full_build_lists(sphb200_ctx* ctx, bool from_stream = false);
 int sph_full_configure(sphb200_ctx* ctx);
 // sph_reduce.cu (in sph_grid.cu)
 int sph_reset_scalars(sphb200_ctx* ctx);
