@@ -134,6 +134,39 @@ int sphb200_scene_sphere(const SphParams* p, float* pos_xyz, float* vel_xyz);
 int sphb200_scene_lattice(int nx, int ny, int nz, float spacing, const float origin[3],
                           uint32_t seed, long long first_id, long long count, float* pos_xyz);
 
+/* Named throughput scenes (BASELINE.json configs 2-5; SURVEY 8(d) scene rule): a block of
+ * fluid on the jittered lattice of spacing d = h (4 pi / (3 nu))^(1/3), h = 0.1, at rest,
+ * under uniform gravity (0,-9.8,0) in a box with reflecting walls -- the two switches the
+ * reference's GUI rows `gravity` / `damping` were meant to drive (sphconfig.cpp:76-95) but its
+ * physics never reads. */
+enum
+{
+   SPHB200_SCENE_DAMBREAK_16K = 0,   /*  32 x  16 x  32 sites, box  20 x  8 x   8 voxels (parity tests)  */
+   SPHB200_SCENE_DAMBREAK_128K = 1,  /*  64 x  32 x  64 sites, box  40 x 16 x  16 voxels                 */
+   SPHB200_SCENE_DAMBREAK_1M = 2,    /* 128 x  64 x 128 sites, box  80 x 32 x  32 voxels (config 2)      */
+   SPHB200_SCENE_DAMBREAK_16M = 3,   /* 256 x 128 x 512 sites, box 160 x 64 x 128 voxels (config 3)      */
+   SPHB200_SCENE_BOXDROP_16M = 4     /* the same block lifted off the floor and centred (config 4, per GPU) */
+};
+
+typedef struct SphSceneLattice
+{
+   int nx, ny, nz;            /* lattice sites; particle id = (z*ny + y)*nx + x          */
+   float spacing;             /* d                                                       */
+   float origin[3];           /* min corner of the block                                 */
+   uint32_t seed;             /* jitter hash seed (42)                                   */
+} SphSceneLattice;
+
+/* Fills `p` (from sphb200_default_params values: particle count, voxel grid -- grown when a
+ * sparse lattice, nu < 40, is taller than the nominal box --, FULL neighbour mode, uniform
+ * gravity + walls on, central mass off, rest density 1/d^3 of the lattice, examine_count
+ * sized for nu) and the lattice descriptor of the scene at `nu` mean neighbours (40 = the
+ * "default smoothing radius" of configs 2-4; 30 / 60 / 120 = config 5). */
+int sphb200_scene_config(int scene, float nu, SphParams* p, SphSceneLattice* lattice);
+/* positions (and zero velocities, when vel_xyz != NULL) of particles first_id ..
+ * first_id + count - 1 of a configured scene */
+int sphb200_scene_generate(const SphSceneLattice* lattice, long long first_id, long long count,
+                           float* pos_xyz, float* vel_xyz);
+
 /* ---- state: host <-> HBM (Particle arrays, particle.h:13-18) ----------------- */
 /* xyz-interleaved host arrays of particle_count entries; mass may be NULL (=1) */
 int sphb200_upload_state(sphb200_ctx* ctx, const float* pos_xyz, const float* vel_xyz, const float* mass);

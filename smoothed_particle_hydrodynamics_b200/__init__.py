@@ -8,6 +8,7 @@ contains no compute and no CPU fallback -- without the built library or without
 a CUDA device every entry point raises.
 """
 from .binding import (  # noqa: F401
-    FULL, SAMPLED, SPH, Field, SlabSPH, SphDerived, SphError, SphParams, default_params, derive, lib, lib_path,
-    scene_lattice, scene_sphere, slab_layers, step_virtual_slabs, voxel_layer,
+    FULL, SAMPLED, SCENES, SPH, Field, SlabSPH, SphDerived, SphError, SphParams, SphSceneLattice, default_params, derive,
+    lib, lib_path, scene_config, scene_generate, scene_lattice, scene_sphere, slab_layers, step_virtual_slabs,
+    voxel_layer,
 )

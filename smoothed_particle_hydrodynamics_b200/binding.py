@@ -56,6 +56,14 @@ class SphDerived(C.Structure):
     ]
 
 
+class SphSceneLattice(C.Structure):
+    _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("spacing", C.c_float),
+                ("origin", C.c_float * 3), ("seed", C.c_uint32)]
+
+
+SCENES = {"dambreak_16k": 0, "dambreak_128k": 1, "dambreak_1m": 2, "dambreak_16m": 3, "boxdrop_16m": 4}
+
+
 class Field:
     POSITION, VELOCITY, MASS, DENSITY, ACCELERATION, NEIGHBOR_COUNT, VOXEL_ID, VOXEL_COORD = range(8)
     GRID_START, GRID_MEMBERS, CELL_COUNT, NEIGHBOR_INDEX, NEIGHBOR_DISTANCE, FINE_KEY = range(8, 14)
@@ -76,6 +84,8 @@ API = [
     ("sphb200_scene_sphere", [C.POINTER(SphParams), _VP, _VP], C.c_int),
     ("sphb200_scene_lattice", [C.c_int, C.c_int, C.c_int, C.c_float, C.POINTER(C.c_float), C.c_uint32,
                                C.c_longlong, C.c_longlong, _VP], C.c_int),
+    ("sphb200_scene_config", [C.c_int, C.c_float, C.POINTER(SphParams), C.POINTER(SphSceneLattice)], C.c_int),
+    ("sphb200_scene_generate", [C.POINTER(SphSceneLattice), C.c_longlong, C.c_longlong, _VP, _VP], C.c_int),
     ("sphb200_upload_state", [_VP, _VP, _VP, _VP], C.c_int),
     ("sphb200_download", [_VP, C.c_int, _VP, C.c_size_t], C.c_int),
     ("sphb200_step", [_VP, C.c_int], C.c_int),
@@ -182,6 +192,29 @@ def scene_lattice(nx, ny, nz, spacing, origin=(0.0, 0.0, 0.0), seed=42, first_id
     rc = lib().sphb200_scene_lattice(nx, ny, nz, float(spacing), org, seed, first_id, count, _ptr(pos))
     if rc:
         raise SphError(rc, "scene_lattice: bad arguments")
+    return pos
+
+
+def scene_config(name, nu=40.0, **overrides):
+    """(SphParams, SphSceneLattice) of a named throughput scene (sphb200_scene_config)."""
+    p, lat = SphParams(), SphSceneLattice()
+    rc = lib().sphb200_scene_config(SCENES[name] if isinstance(name, str) else int(name), float(nu),
+                                    C.byref(p), C.byref(lat))
+    if rc:
+        raise SphError(rc, "scene_config: unknown scene or bad nu")
+    _apply(p, overrides)
+    return p, lat
+
+
+def scene_generate(lat, first_id=0, count=None, out=None, vel_out=None):
+    """Positions (float32 [count,3]) of a configured scene; vel_out, when given, is zeroed."""
+    if count is None:
+        count = lat.nx * lat.ny * lat.nz - first_id
+    pos = out if out is not None else np.empty((count, 3), np.float32)
+    rc = lib().sphb200_scene_generate(C.byref(lat), first_id, count, _ptr(pos),
+                                      _ptr(vel_out) if vel_out is not None else None)
+    if rc:
+        raise SphError(rc, "scene_generate: bad arguments")
     return pos
 
 

@@ -13,6 +13,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "sphb200.h"
 
@@ -92,6 +93,76 @@ int sphb200_scene_lattice(int nx, int ny, int nz, float spacing, const float ori
       }
    }
    return SPHB200_OK;
+}
+
+namespace
+{
+struct SceneRow
+{
+   int sites[3], grid[3], origin_vox[3];
+};
+// SURVEY 8(d) configs 2-4 (+ two small cases for the parity tests), at nu = 40
+const SceneRow kScenes[] = {
+   {{32, 16, 32}, {20, 8, 8}, {0, 0, 0}},          // DAMBREAK_16K
+   {{64, 32, 64}, {40, 16, 16}, {0, 0, 0}},        // DAMBREAK_128K
+   {{128, 64, 128}, {80, 32, 32}, {0, 0, 0}},      // DAMBREAK_1M
+   {{256, 128, 512}, {160, 64, 128}, {0, 0, 0}},   // DAMBREAK_16M
+   {{256, 128, 512}, {160, 64, 128}, {49, 16, 3}}, // BOXDROP_16M
+};
+}  // namespace
+
+int sphb200_scene_config(int scene, float nu, SphParams* p, SphSceneLattice* lat)
+{
+   if (scene < 0 || scene >= (int)(sizeof(kScenes) / sizeof(kScenes[0])) || !p || !lat || !(nu > 0.0f))
+      return SPHB200_E_INVALID;
+   const SceneRow& r = kScenes[scene];
+   int rc = sphb200_default_params(p);
+   if (rc)
+      return rc;
+   // d = h (4 pi / (3 nu))^(1/3) in double, rounded once; h is the nominal 0.1
+   const float d = (float)(0.1 * pow(4.0 * M_PI / (3.0 * (double)nu), 1.0 / 3.0));
+   memset(lat, 0, sizeof(*lat));
+   lat->nx = r.sites[0];
+   lat->ny = r.sites[1];
+   lat->nz = r.sites[2];
+   lat->spacing = d;
+   lat->seed = 42u;
+   const float voxel = 0.2f;
+   int grid[3];
+   for (int k = 0; k < 3; k++)
+   {
+      lat->origin[k] = (float)((double)r.origin_vox[k] * 0.2);
+      // sparser lattices are taller than the nominal box: grow it (config 5)
+      int need = (int)ceil((double)lat->origin[k] / 0.2 + (double)r.sites[k] * (double)d / 0.2) + 2;
+      grid[k] = need > r.grid[k] ? need : r.grid[k];
+   }
+   (void)voxel;
+   p->particle_count = r.sites[0] * r.sites[1] * r.sites[2];
+   p->grid_x = grid[0];
+   p->grid_y = grid[1];
+   p->grid_z = grid[2];
+   p->neighbor_mode = SPHB200_NEIGHBORS_FULL;
+   p->use_uniform_gravity = 1;
+   p->use_wall_collision = 1;
+   p->central_mass = 0.0f;
+   p->gravity[0] = 0.0f;
+   p->gravity[1] = -9.8f;
+   p->gravity[2] = 0.0f;
+   p->rho0 = 1.0f / (d * d * d);          // rest density of the lattice (unit masses)
+   p->examine_count = nu <= 40.0f ? 96 : (int)(nu * 1.6f) + 32;
+   return SPHB200_OK;
+}
+
+int sphb200_scene_generate(const SphSceneLattice* lat, long long first_id, long long count, float* pos_xyz,
+                           float* vel_xyz)
+{
+   if (!lat)
+      return SPHB200_E_INVALID;
+   int rc = sphb200_scene_lattice(lat->nx, lat->ny, lat->nz, lat->spacing, lat->origin, lat->seed, first_id, count,
+                                  pos_xyz);
+   if (rc == SPHB200_OK && vel_xyz)
+      memset(vel_xyz, 0, sizeof(float) * 3 * (size_t)count);
+   return rc;
 }
 
 }  // extern "C"

@@ -68,6 +68,32 @@ def test_lattice_scene_matches_numpy_restatement():
         S.scene_lattice(4, 4, 4, d, first_id=60, count=10)
 
 
+def test_named_scenes_match_the_scene_rule_tables():
+    """sphb200_scene_config / _generate (dam-break, box-drop; configs 2-5) against the independent
+    numpy restatement of the scene rule in oracle/scenes.py: sites, grown box, spacing, rest
+    density and every position bit for bit."""
+    for name in S.SCENES:
+        cfg = scenes.CONFIGS[name]
+        for nu in (30.0, 40.0, 60.0, 120.0):
+            p, lat = S.scene_config(name, nu)
+            d = scenes.lattice_spacing(0.1, nu)
+            sp = scenes.scene_params(nu=nu)
+            origin = [v * 0.2 for v in cfg["origin_vox"]]
+            need = [int(np.ceil(o / 0.2 + s * float(d) / 0.2)) + 2 for o, s in zip(origin, cfg["sites"])]
+            assert (lat.nx, lat.ny, lat.nz) == cfg["sites"] and np.float32(lat.spacing) == d
+            assert (p.grid_x, p.grid_y, p.grid_z) == tuple(max(g, m) for g, m in zip(cfg["grid"], need))
+            assert np.float32(p.rho0) == np.float32(sp["rho0"]) and p.particle_count == np.prod(cfg["sites"])
+            assert (p.neighbor_mode, p.use_uniform_gravity, p.use_wall_collision) == (S.FULL, 1, 1)
+            assert tuple(p.gravity) == (0.0, np.float32(-9.8), 0.0) and p.central_mass == 0.0
+            assert np.array_equal(np.float32(origin), np.float32(list(lat.origin)))
+    p, lat = S.scene_config("boxdrop_16m")
+    a = S.scene_generate(lat, first_id=123456, count=4096)
+    b = scenes.lattice_scene(256, 128, 512, lat.spacing, origin=list(lat.origin), first_id=123456, count=4096)
+    assert np.array_equal(a, b)
+    with pytest.raises(S.SphError):
+        S.scene_config(99)
+
+
 def test_invalid_params_are_rejected():
     for kw in (dict(examine_count=4), dict(h=0.0), dict(grid=(0, 4, 4)), dict(neighbor_mode=7),
                dict(grid=(2048, 2048, 2048))):
