@@ -197,6 +197,42 @@ int sphb200_get_neighbor_stats(sphb200_ctx* ctx, long long* total, int* max_coun
 /* ms of the last step: voxelize, findNeighbors, density, pressure, acceleration,
  * integrate -- the six slots of SPH::updateElapsed (sph.h:73-81) */
 int sphb200_get_timings(sphb200_ctx* ctx, float ms[6]);
+/* everything above in ONE call and one synchronisation (what SPH::step() of the facade needs
+ * after every step: sph.cpp:226-232, 292-299, 1001-1008) */
+typedef struct SphStepReport
+{
+   float e_kin, e_pot;
+   long long nbr_total;
+   int nbr_max, nbr_min;
+   float phase_ms[6];          /* zeros unless enable_timers                              */
+   long long step_index;       /* steps this context has run since creation               */
+} SphStepReport;
+int sphb200_get_step_report(sphb200_ctx* ctx, SphStepReport* out);
+
+/* ---- viewer snapshots: the readback contract of the GL view -----------------------------
+ * Visualization::paintGL runs on a 16 ms timer (visualization.cpp:24-33) and reads
+ * getParticles()->mPosition[3i+k] for every particle (137-163) and getGrid()[c].count() for
+ * every voxel (166-213), from the GUI thread, while the worker thread steps.  With the state
+ * in HBM that becomes an asynchronous snapshot: sphb200_snapshot_request (stepping thread)
+ * packs the positions (and per-voxel counts) behind the steps already submitted and starts a
+ * device -> pinned-host copy on a side stream -- the step stream does not wait for PCIe --;
+ * sphb200_snapshot_read (ANY thread, also while the stepping thread is inside sphb200_step)
+ * copies the newest COMPLETED snapshot into the caller's arrays.  Two pinned buffers; a
+ * request that finds its buffer still in flight or being read is dropped (a skipped frame),
+ * never waited for.  Single-GPU contexts only. */
+enum
+{
+   SPHB200_SNAP_POSITIONS = 1,    /* float[3N], Particle::mPosition layout                 */
+   SPHB200_SNAP_CELL_COUNTS = 2   /* int[cells], mGrid[c].count() of the current positions */
+};
+int sphb200_snapshot_request(sphb200_ctx* ctx, int what);
+/* *step_index: in = the snapshot the caller already has (-1: none), out = the one copied.
+ * Returns SPHB200_OK with *step_index unchanged when there is nothing newer.  wait != 0
+ * blocks until the most recently requested snapshot is complete.  Either destination may be
+ * NULL. */
+int sphb200_snapshot_read(sphb200_ctx* ctx, int wait, float* pos_xyz, size_t pos_bytes, int* cell_counts,
+                          size_t count_bytes, long long* step_index);
+
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 int sphb200_get_launch_count(const sphb200_ctx* ctx, long long* launches);
 

@@ -56,6 +56,11 @@ class SphDerived(C.Structure):
     ]
 
 
+class SphStepReport(C.Structure):
+    _fields_ = [("e_kin", C.c_float), ("e_pot", C.c_float), ("nbr_total", C.c_longlong), ("nbr_max", C.c_int),
+                ("nbr_min", C.c_int), ("phase_ms", C.c_float * 6), ("step_index", C.c_longlong)]
+
+
 class SphSceneLattice(C.Structure):
     _fields_ = [("nx", C.c_int), ("ny", C.c_int), ("nz", C.c_int), ("spacing", C.c_float),
                 ("origin", C.c_float * 3), ("seed", C.c_uint32)]
@@ -93,6 +98,9 @@ API = [
     ("sphb200_step_host", [_VP, _VP, _VP, _VP], C.c_int),
     ("sphb200_build_neighbor_lists", [_VP], C.c_int),
     ("sphb200_build_neighbor_lists_visited", [_VP], C.c_int),
+    ("sphb200_get_step_report", [_VP, C.POINTER(SphStepReport)], C.c_int),
+    ("sphb200_snapshot_request", [_VP, C.c_int], C.c_int),
+    ("sphb200_snapshot_read", [_VP, C.c_int, _VP, C.c_size_t, _VP, C.c_size_t, C.POINTER(C.c_longlong)], C.c_int),
     ("sphb200_get_energies", [_VP, C.POINTER(C.c_float), C.POINTER(C.c_float)], C.c_int),
     ("sphb200_get_neighbor_stats", [_VP, C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_int)], C.c_int),
     ("sphb200_get_timings", [_VP, C.POINTER(C.c_float)], C.c_int),
@@ -338,6 +346,26 @@ class SPH:
             self._check(self._lib.sphb200_build_neighbor_lists_visited(self._h))
         else:
             self._check(self._lib.sphb200_build_neighbor_lists(self._h))
+
+    def step_report(self):
+        r = SphStepReport()
+        self._check(self._lib.sphb200_get_step_report(self._h, C.byref(r)))
+        return r
+
+    def snapshot_request(self, positions=True, cell_counts=False):
+        self._check(self._lib.sphb200_snapshot_request(self._h, (1 if positions else 0) | (2 if cell_counts else 0)))
+
+    def snapshot_read(self, have=-1, wait=False, positions=True, cell_counts=False):
+        """(step_index, pos[n,3] or None, counts[cells] or None) of the newest completed snapshot;
+        step_index == have means there is nothing newer."""
+        p = self.params
+        n, cells = p.particle_count, p.grid_x * p.grid_y * p.grid_z
+        pos = np.empty((n, 3), np.float32) if positions else None
+        cnt = np.empty(cells, np.int32) if cell_counts else None
+        idx = C.c_longlong(have)
+        self._check(self._lib.sphb200_snapshot_read(self._h, 1 if wait else 0, _ptr(pos), pos.nbytes if positions else 0,
+                                                    _ptr(cnt), cnt.nbytes if cell_counts else 0, C.byref(idx)))
+        return idx.value, pos, cnt
 
     def energies(self):
         ek, ep = C.c_float(), C.c_float()

@@ -64,15 +64,18 @@ def build(force=False, verbose=False):
 
 HOST = os.path.join(HERE, "host")
 HEADLESS = os.path.join(HERE, "sph_headless")
+FACADE_CHECK = os.path.join(HERE, "facade_check")
 
 
 def build_host(force=False):
     """The C++ facade (host/sph.cpp, reference `class SPH` interface) + the headless driver."""
-    srcs = [os.path.join(HOST, f) for f in ("sph.cpp", "headless_main.cpp")]
-    deps = srcs + [os.path.join(HOST, f) for f in ("sph.h", "particle.h", "vec3.h")] + [LIB]
-    if force or _newer(HEADLESS, deps):
-        subprocess.check_call(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), "-I", HOST] + srcs +
-                              ["-L", HERE, "-lsphb200", "-Wl,-rpath,$ORIGIN", "-o", HEADLESS])
+    hdrs = [os.path.join(HOST, f) for f in ("sph.h", "particle.h", "vec3.h")] + [LIB]
+    # sph_headless = the reference's `./sph r`; facade_check = GPU checks of the readback path (tests/test_gpu_headless.py)
+    for exe, main in ((HEADLESS, "headless_main.cpp"), (FACADE_CHECK, "facade_check.cpp")):
+        srcs = [os.path.join(HOST, f) for f in ("sph.cpp", main)]
+        if force or _newer(exe, srcs + hdrs):
+            subprocess.check_call(["g++", "-std=c++11", "-O2", "-pthread", "-I", os.path.join(ROOT, "include"), "-I", HOST] +
+                                  srcs + ["-L", HERE, "-lsphb200", "-Wl,-rpath,$ORIGIN", "-o", exe])
     return HEADLESS
 
 

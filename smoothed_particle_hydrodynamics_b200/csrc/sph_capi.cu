@@ -156,6 +156,56 @@ int fetch_scalars(sphb200_ctx* ctx)
    return SPHB200_OK;
 }
 
+void snapshots_free(sphb200_ctx* ctx)
+{
+   sphb200_ctx::Snapshots* sn = ctx->snap;
+   if (!sn)
+      return;
+   if (sn->stream)
+   {
+      cudaStreamSynchronize(sn->stream);
+      cudaStreamDestroy(sn->stream);
+   }
+   if (sn->staged) cudaEventDestroy(sn->staged);
+   for (int b = 0; b < 2; b++)
+   {
+      if (sn->done[b]) cudaEventDestroy(sn->done[b]);
+      if (sn->host_pos[b]) cudaFreeHost(sn->host_pos[b]);
+      if (sn->host_cnt[b]) cudaFreeHost(sn->host_cnt[b]);
+   }
+   if (sn->dev_pos) cudaFree(sn->dev_pos);
+   if (sn->dev_cnt) cudaFree(sn->dev_cnt);
+   delete sn;
+   ctx->snap = nullptr;
+}
+
+int snapshots_init(sphb200_ctx* ctx)
+{
+   if (ctx->snap && ctx->snap->ready)
+      return SPHB200_OK;
+   sphb200_ctx::Snapshots* sn = ctx->snap ? ctx->snap : new (std::nothrow) sphb200_ctx::Snapshots();
+   if (!sn)
+      return sph_fail(ctx, SPHB200_E_INVALID, "out of host memory");
+   ctx->snap = sn;
+   const size_t n = (size_t)(ctx->capacity > 0 ? ctx->capacity : 1), cells = (size_t)ctx->cells_voxel;
+   SPH_CUDA_CHECK(ctx, cudaStreamCreateWithFlags(&sn->stream, cudaStreamNonBlocking));
+   SPH_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&sn->staged, cudaEventDisableTiming));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&sn->dev_pos, sizeof(float) * 3 * n));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&sn->dev_cnt, sizeof(uint32_t) * cells));
+   for (int b = 0; b < 2; b++)
+   {
+      SPH_CUDA_CHECK(ctx, cudaEventCreateWithFlags(&sn->done[b], cudaEventDisableTiming));
+      SPH_CUDA_CHECK(ctx, cudaMallocHost((void**)&sn->host_pos[b], sizeof(float) * 3 * n));
+      SPH_CUDA_CHECK(ctx, cudaMallocHost((void**)&sn->host_cnt[b], sizeof(int) * cells));
+      sn->step[b] = -1;
+      sn->what[b] = 0;
+      sn->in_flight[b] = false;
+   }
+   sn->newest = -1;
+   sn->ready = true;
+   return SPHB200_OK;
+}
+
 }  // namespace
 
 int sph_fail(sphb200_ctx* ctx, int code, const std::string& msg)
@@ -250,6 +300,7 @@ static int step_graph(sphb200_ctx* ctx, int n_steps)
    {
       SPH_CUDA_CHECK(ctx, cudaGraphLaunch(ctx->graph_exec, st));
       ctx->launches += ctx->graph_launches;
+      ctx->steps_done++;
    }
    // host-side view of what a step leaves behind (the capture ran the same code once)
    const bool full = ctx->params.neighbor_mode == SPHB200_NEIGHBORS_FULL;
@@ -410,6 +461,8 @@ int sphb200_destroy(sphb200_ctx* ctx)
       cudaEventDestroy(ctx->upload_ev[0]);
       cudaEventDestroy(ctx->upload_ev[1]);
    }
+   snapshots_free(ctx);
+   if (ctx->h_report) cudaFreeHost(ctx->h_report);
    if (ctx->tex_posA) cudaDestroyTextureObject(ctx->tex_posA);
    if (ctx->tex_velB) cudaDestroyTextureObject(ctx->tex_velB);
    sph_grid_free(ctx);
@@ -551,6 +604,7 @@ int sphb200_step(sphb200_ctx* ctx, int n_steps)
       if (rc)
          return rc;
       ctx->stepped = true;
+      ctx->steps_done++;
    }
    return SPHB200_OK;
 }
@@ -731,6 +785,8 @@ static int step_host_overlapped(sphb200_ctx* ctx, const float* pos_xyz, const fl
    int rc = sph_step_full(ctx);
    ctx->deferred_vel_event = nullptr;
    ctx->stepped = rc == SPHB200_OK;
+   if (rc == SPHB200_OK)
+      ctx->steps_done++;
    return rc;
 }
 
@@ -847,6 +903,147 @@ int sphb200_get_timings(sphb200_ctx* ctx, float ms[6])
       else
          cudaGetLastError();
    }
+   return SPHB200_OK;
+}
+
+int sphb200_get_step_report(sphb200_ctx* ctx, SphStepReport* out)
+{
+   if (!ctx || !out)
+      return sph_fail(ctx, SPHB200_E_INVALID, "null argument");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   if (!ctx->h_report)
+      SPH_CUDA_CHECK(ctx, cudaMallocHost((void**)&ctx->h_report, sizeof(StepScalars)));
+   SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_report, ctx->d_scalars, sizeof(StepScalars), cudaMemcpyDeviceToHost,
+                                       ctx->stream));
+   SPH_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+   int rc = sph_comm_check(ctx);
+   if (rc)
+      return rc;
+   ctx->h_scalars = *ctx->h_report;
+   out->e_kin = (float)ctx->h_scalars.e_kin;
+   out->e_pot = (float)ctx->h_scalars.e_pot;
+   out->nbr_total = (long long)ctx->h_scalars.nbr_total;
+   out->nbr_max = ctx->h_scalars.nbr_max;
+   out->nbr_min = ctx->h_scalars.nbr_min;
+   out->step_index = ctx->steps_done;
+   for (int i = 0; i < 6; i++)
+      out->phase_ms[i] = 0.0f;
+   if (ctx->params.enable_timers && ctx->stepped)
+      for (int i = 0; i < 6; i++)
+      {
+         float t = 0.0f;
+         if (cudaEventElapsedTime(&t, ctx->ev[i], ctx->ev[i + 1]) == cudaSuccess)
+            out->phase_ms[i] = t;
+         else
+            cudaGetLastError();
+      }
+   return SPHB200_OK;
+}
+
+int sphb200_snapshot_request(sphb200_ctx* ctx, int what)
+{
+   if (!ctx || !(what & (SPHB200_SNAP_POSITIONS | SPHB200_SNAP_CELL_COUNTS)))
+      return sph_fail(ctx, SPHB200_E_INVALID, "snapshot_request: bad argument");
+   if (ctx->comm)
+      return sph_fail(ctx, SPHB200_E_INVALID, "snapshot_request: single-GPU contexts only");
+   SPH_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+   int rc = snapshots_init(ctx);
+   if (rc)
+      return rc;
+   sphb200_ctx::Snapshots* sn = ctx->snap;
+   // a reader copying out of a buffer right now: skip this frame instead of stalling the steps
+   std::unique_lock<std::mutex> lk(sn->lock, std::try_to_lock);
+   if (!lk.owns_lock())
+      return SPHB200_OK;
+   for (int b = 0; b < 2; b++)
+      if (sn->in_flight[b] && cudaEventQuery(sn->done[b]) == cudaSuccess)
+         sn->in_flight[b] = false;
+   cudaGetLastError();   // cudaErrorNotReady is not an error
+   // the buffer that does not hold the newest complete snapshot
+   int target = sn->newest < 0 ? 0 : 1 - sn->newest;
+   if (sn->in_flight[target])
+      target = 1 - target;                    // the other one finished in the meantime?
+   if (sn->in_flight[target] || sn->in_flight[1 - target])
+      return SPHB200_OK;                      // a copy is still on the wire (one staging buffer): drop the frame
+   cudaStream_t st = ctx->stream;
+   const int n = ctx->n_local;
+   if ((what & SPHB200_SNAP_POSITIONS) && n > 0)
+   {
+      k_unpack_xyz<<<blocks_for(n), kThreads, 0, st>>>(n, ctx->pos4, sn->dev_pos);
+      ctx->launches++;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   }
+   if (what & SPHB200_SNAP_CELL_COUNTS)
+   {
+      rc = sph_grid_voxel_histogram(ctx, sn->dev_cnt);
+      if (rc)
+         return rc;
+   }
+   SPH_CUDA_CHECK(ctx, cudaEventRecord(sn->staged, st));
+   SPH_CUDA_CHECK(ctx, cudaStreamWaitEvent(sn->stream, sn->staged, 0));
+   if ((what & SPHB200_SNAP_POSITIONS) && n > 0)
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(sn->host_pos[target], sn->dev_pos, sizeof(float) * 3 * (size_t)n,
+                                          cudaMemcpyDeviceToHost, sn->stream));
+   if (what & SPHB200_SNAP_CELL_COUNTS)
+      SPH_CUDA_CHECK(ctx, cudaMemcpyAsync(sn->host_cnt[target], sn->dev_cnt, sizeof(int) * (size_t)ctx->cells_voxel,
+                                          cudaMemcpyDeviceToHost, sn->stream));
+   SPH_CUDA_CHECK(ctx, cudaEventRecord(sn->done[target], sn->stream));
+   // the next step may overwrite pos4 as soon as the pack kernel has run (stream order); the
+   // staging buffers are reused only after this copy (in_flight above)
+   sn->in_flight[target] = true;
+   sn->what[target] = what;
+   sn->step[target] = ctx->steps_done;
+   sn->newest = target;
+   return SPHB200_OK;
+}
+
+int sphb200_snapshot_read(sphb200_ctx* ctx, int wait, float* pos_xyz, size_t pos_bytes, int* cell_counts,
+                          size_t count_bytes, long long* step_index)
+{
+   if (!ctx || !step_index)
+      return sph_fail(ctx, SPHB200_E_INVALID, "snapshot_read: null argument");
+   sphb200_ctx::Snapshots* sn = ctx->snap;
+   if (!sn || !sn->ready)
+      return SPHB200_OK;                      // nothing requested yet
+   // no CUDA call below touches the context's stream: safe beside a running sphb200_step
+   std::lock_guard<std::mutex> lk(sn->lock);
+   int b = sn->newest;
+   if (b < 0)
+      return SPHB200_OK;
+   if (sn->in_flight[b])
+   {
+      if (wait)
+      {
+         if (cudaEventSynchronize(sn->done[b]) != cudaSuccess)
+            return sph_fail(ctx, SPHB200_E_CUDA, "snapshot_read: copy failed");
+         sn->in_flight[b] = false;
+      }
+      else if (cudaEventQuery(sn->done[b]) == cudaSuccess)
+         sn->in_flight[b] = false;
+      else
+      {
+         cudaGetLastError();
+         b = 1 - b;                           // the previous snapshot, if it is complete
+         if (sn->step[b] < 0 || sn->in_flight[b])
+            return SPHB200_OK;
+      }
+   }
+   if (sn->step[b] <= *step_index)
+      return SPHB200_OK;                      // the caller already has it
+   const size_t n = (size_t)ctx->n_local, cells = (size_t)ctx->cells_voxel;
+   if (pos_xyz && (sn->what[b] & SPHB200_SNAP_POSITIONS))
+   {
+      if (pos_bytes < sizeof(float) * 3 * n)
+         return sph_fail(ctx, SPHB200_E_INVALID, "snapshot_read: position destination too small");
+      memcpy(pos_xyz, sn->host_pos[b], sizeof(float) * 3 * n);
+   }
+   if (cell_counts && (sn->what[b] & SPHB200_SNAP_CELL_COUNTS))
+   {
+      if (count_bytes < sizeof(int) * cells)
+         return sph_fail(ctx, SPHB200_E_INVALID, "snapshot_read: count destination too small");
+      memcpy(cell_counts, sn->host_cnt[b], sizeof(int) * cells);
+   }
+   *step_index = sn->step[b];
    return SPHB200_OK;
 }
 

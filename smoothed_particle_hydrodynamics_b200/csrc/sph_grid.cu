@@ -412,6 +412,22 @@ int sph_refresh_voxel_ids(sphb200_ctx* ctx)
    return SPHB200_OK;
 }
 
+// mGrid[c].count() for every voxel, into a device array (enqueued on the context's stream)
+int sph_grid_voxel_histogram(sphb200_ctx* ctx, uint32_t* d_counts)
+{
+   int rc = sph_refresh_voxel_ids(ctx);
+   if (rc)
+      return rc;
+   SPH_CUDA_CHECK(ctx, cudaMemsetAsync(d_counts, 0, sizeof(uint32_t) * (size_t)ctx->cells_voxel, ctx->stream));
+   if (ctx->n_local > 0)
+   {
+      k_histogram<<<blocks_for(ctx->n_local), kThreads, 0, ctx->stream>>>(ctx->n_local, ctx->voxel_id, d_counts);
+      ctx->launches++;
+      SPH_CUDA_CHECK(ctx, cudaGetLastError());
+   }
+   return SPHB200_OK;
+}
+
 int sph_download_grid(sphb200_ctx* ctx, int field, void* dst, size_t bytes)
 {
    const int n = ctx->n_local;

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 
 #include "sphb200.h"
@@ -163,6 +164,27 @@ struct sphb200_ctx
    bool stepped;
 
    SlabComm* comm;
+
+   long long steps_done;       // steps run since creation (snapshot / report stamps)
+   StepScalars* h_report;      // pinned copy of d_scalars (sphb200_get_step_report)
+
+   // viewer snapshots (sphb200_snapshot_request / _read)
+   struct Snapshots
+   {
+      std::mutex lock;            // buffer roles below; read() holds it while copying out
+      cudaStream_t stream;        // side stream of the D2H copies
+      cudaEvent_t staged;         // staging buffers written (step stream)
+      cudaEvent_t done[2];        // copy into pinned buffer b complete (side stream)
+      float* dev_pos;             // float[3 * capacity] staging
+      uint32_t* dev_cnt;          // uint32[cells_voxel] staging
+      float* host_pos[2];         // pinned
+      int* host_cnt[2];           // pinned
+      int what[2];
+      long long step[2];          // step index of the snapshot in buffer b (-1: empty)
+      bool in_flight[2];
+      int newest;                 // buffer of the most recent request (-1: none)
+      bool ready;
+   } * snap;
 };
 
 #define SPH_CUDA_CHECK(ctx, expr)                                                        \
@@ -181,6 +203,7 @@ DevParams sph_dev_params(const sphb200_ctx* ctx);
 int sph_bin_and_sort(sphb200_ctx* ctx, bool fine);
 int sph_download_grid(sphb200_ctx* ctx, int field, void* dst, size_t bytes);
 int sph_refresh_voxel_ids(sphb200_ctx* ctx);
+int sph_grid_voxel_histogram(sphb200_ctx* ctx, uint32_t* d_counts);   // per-voxel particle counts of the current positions
 int sph_grid_setup(sphb200_ctx* ctx);
 // sph_sampled.cu
 int sph_step_sampled(sphb200_ctx* ctx);

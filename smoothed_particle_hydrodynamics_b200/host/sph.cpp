@@ -4,6 +4,7 @@
 #include <sys/stat.h>
 #include <sys/types.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -20,6 +21,12 @@ SphParams referenceDefaults()
    sphb200_default_params(&p);
    p.enable_timers = 1;   // the reference times every phase of every step (sph.cpp:209-290)
    return p;
+}
+
+long long nowNs()
+{
+   return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch())
+      .count();
 }
 }  // namespace
 
@@ -45,6 +52,12 @@ void SPH::init(const SphParams& params, bool sphereScene, int device)
    mParams = params;
    mSrcParticles = nullptr;
    mReadback = ReadbackPositions;
+   mReadbackIntervalMs = 0;
+   mGridMembership = false;
+   mDefaultDamping = params.damping;
+   mSnapshotHave = mGridHave = -1;
+   mStepIndex = 0;
+   mLastRequestNs = 0;
    mKineticEnergyTotal = mPotentialEnergyTotal = 0.0f;
    timeVoxelize = timeFindNeighbors = timeComputeDensity = timeComputePressure = timeComputeAcceleration =
       timeIntegrate = 0;
@@ -106,6 +119,7 @@ void SPH::stopSimulation()
 
 void SPH::uploadState(const float* posXyz, const float* velXyz, const float* mass)
 {
+   std::lock_guard<std::mutex> ctxLock(mCtxMutex);
    check(sphb200_upload_state(mCtx, posXyz, velXyz, mass), "sphb200_upload_state");
    const size_t n = (size_t)mParams.particle_count;
    std::copy(posXyz, posXyz + 3 * n, mSrcParticles->mPosition.begin());
@@ -118,9 +132,15 @@ void SPH::refreshParticles(Readback what)
 {
    if (what == ReadbackNone)
       return;
+   std::lock_guard<std::mutex> ctxLock(mCtxMutex);
    Particle* p = mSrcParticles;
    const size_t n = (size_t)mParams.particle_count;
-   check(sphb200_download(mCtx, SPHB200_F_POSITION, p->mPosition.data(), sizeof(float) * 3 * n), "download position");
+   {
+      // a snapshot older than this download must not overwrite it later
+      std::lock_guard<std::mutex> lock(mMirrorMutex);
+      check(sphb200_download(mCtx, SPHB200_F_POSITION, p->mPosition.data(), sizeof(float) * 3 * n), "download position");
+      mSnapshotHave = mStepIndex;
+   }
    if (what != ReadbackAll)
       return;
    check(sphb200_download(mCtx, SPHB200_F_VELOCITY, p->mVelocity.data(), sizeof(float) * 3 * n), "download velocity");
@@ -132,25 +152,35 @@ void SPH::refreshParticles(Readback what)
          "download neighbour count");
 }
 
-// One time step (reference: sph.cpp:190-304).  All five phases run on the GPU;
-// afterwards the six phase times, the energies and the neighbour statistics are
-// fetched (a few scalars) and the host mirror is refreshed per the readback policy.
+// One time step (reference: sph.cpp:190-304).  All five phases run on the GPU; afterwards ONE
+// call and one synchronisation fetch the six phase times, the energies and the neighbour
+// statistics (sphb200_get_step_report).  Positions and per-voxel counts for the GL view leave
+// the device as an asynchronous snapshot that the next steps do not wait for.
 void SPH::step()
 {
-   check(sphb200_step(mCtx, 1), "sphb200_step");
-   float ms[6];
-   check(sphb200_get_timings(mCtx, ms), "sphb200_get_timings");
-   // the reference truncates nanoseconds to whole milliseconds (sph.cpp:211, 233, ...)
-   timeVoxelize = (int)ms[0];
-   timeFindNeighbors = (int)ms[1];
-   timeComputeDensity = (int)ms[2];
-   timeComputePressure = (int)ms[3];
-   timeComputeAcceleration = (int)ms[4];
-   timeIntegrate = (int)ms[5];
-   check(sphb200_get_energies(mCtx, &mKineticEnergyTotal, &mPotentialEnergyTotal), "sphb200_get_energies");
-   check(sphb200_get_neighbor_stats(mCtx, &mNeighborTotal, &mNeighborMax, &mNeighborMin),
-         "sphb200_get_neighbor_stats");
-   refreshParticles(mReadback);
+   {
+      std::lock_guard<std::mutex> ctxLock(mCtxMutex);
+      check(sphb200_step(mCtx, 1), "sphb200_step");
+      SphStepReport rep;
+      check(sphb200_get_step_report(mCtx, &rep), "sphb200_get_step_report");
+      // the reference truncates nanoseconds to whole milliseconds (sph.cpp:211, 233, ...)
+      timeVoxelize = (int)rep.phase_ms[0];
+      timeFindNeighbors = (int)rep.phase_ms[1];
+      timeComputeDensity = (int)rep.phase_ms[2];
+      timeComputePressure = (int)rep.phase_ms[3];
+      timeComputeAcceleration = (int)rep.phase_ms[4];
+      timeIntegrate = (int)rep.phase_ms[5];
+      mKineticEnergyTotal = rep.e_kin;
+      mPotentialEnergyTotal = rep.e_pot;
+      mNeighborTotal = rep.nbr_total;
+      mNeighborMax = rep.nbr_max;
+      mNeighborMin = rep.nbr_min;
+      mStepIndex = rep.step_index;
+      if (mReadback == ReadbackPositions)
+         requestSnapshot();
+   }
+   if (mReadback == ReadbackAll)
+      refreshParticles(ReadbackAll);
 #ifdef SPHB200_WITH_QT
    emit updateElapsed(timeVoxelize, timeFindNeighbors, timeComputeDensity, timeComputePressure,
                       timeComputeAcceleration, timeIntegrate);
@@ -162,6 +192,45 @@ void SPH::step()
    if (stepFinished)
       stepFinished();
 #endif
+}
+
+// Throttle of the readback path: at most one snapshot per readback interval (the GL view
+// repaints every 16 ms, visualization.cpp:24-33; a 16.7 M-particle snapshot is 200 MB of PCIe).
+void SPH::requestSnapshot()
+{
+   const long long now = nowNs();
+   if (mReadbackIntervalMs > 0 && mLastRequestNs != 0 && now - mLastRequestNs < 1000000LL * mReadbackIntervalMs)
+      return;
+   mLastRequestNs = now;
+   check(sphb200_snapshot_request(mCtx, SPHB200_SNAP_POSITIONS | SPHB200_SNAP_CELL_COUNTS), "sphb200_snapshot_request");
+}
+
+// newest completed snapshot -> host mirror.  Does not touch the context's stream, so the GUI
+// thread may call it while the worker is inside step().
+bool SPH::pullSnapshot(bool positions, bool counts)
+{
+   std::lock_guard<std::mutex> lock(mMirrorMutex);
+   const int wait = mReadbackIntervalMs == 0 ? 1 : 0;
+   bool fresh = false;
+   if (positions)
+   {
+      long long have = mSnapshotHave;
+      std::vector<float>& pos = mSrcParticles->mPosition;
+      check(sphb200_snapshot_read(mCtx, wait, pos.data(), sizeof(float) * pos.size(), nullptr, 0, &have),
+            "sphb200_snapshot_read");
+      fresh = have != mSnapshotHave;
+      mSnapshotHave = have;
+   }
+   if (counts)
+   {
+      long long have = mGridHave;
+      mGridCounts.resize((size_t)mDerived.grid_cell_count);
+      check(sphb200_snapshot_read(mCtx, wait, nullptr, 0, mGridCounts.data(), sizeof(int) * mGridCounts.size(), &have),
+            "sphb200_snapshot_read");
+      fresh = fresh || have != mGridHave;
+      mGridHave = have;
+   }
+   return fresh;
 }
 
 // The worker loop (reference: sph.cpp:149-187): totalSteps + 1 steps, and the four
@@ -195,9 +264,17 @@ void SPH::run()
              << timeComputePressure << ", " << timeComputeAcceleration << ", " << timeIntegrate << std::endl;
       stepCount++;
    }
+   // snapshots are requested, not waited for: leave the mirror at the final state
+   if (mReadback == ReadbackPositions)
+      refreshParticles(ReadbackPositions);
 }
 
-Particle* SPH::getParticles() { return mSrcParticles; }
+Particle* SPH::getParticles()
+{
+   if (mReadback == ReadbackPositions)
+      pullSnapshot(true, false);
+   return mSrcParticles;
+}
 int SPH::getParticleCount() const { return mParams.particle_count; }
 
 void SPH::getGridCellCounts(int& x, int& y, int& z)
@@ -217,20 +294,42 @@ void SPH::getParticleBounds(float& x, float& y, float& z)
 float SPH::getInteractionRadius2() const { return mDerived.h_scaled2; }
 float SPH::getCellSize() const { return mDerived.cell_size; }
 
-// Per-voxel membership lists of the last binning (reference: QList<uint32_t> mGrid,
-// sph.h:172).  Rebuilt from the device on every call: the GL view calls it once per
-// frame (visualization.cpp:180) and only needs count().
+// mGrid of the reference (QList<uint32_t> per voxel, sph.h:172).  Its one reader, drawVoxels,
+// calls it once per frame and only asks count() of every voxel (visualization.cpp:178-193):
+// the counts come from the newest snapshot (one int per voxel, histogrammed on the device).
+// The member indices are filled only in a Qt build (a QList has no count without members) or
+// after setGridMembership(true): that is a download of every particle index per call.
 SphCellList* SPH::getGrid()
 {
    const int cells = mDerived.grid_cell_count;
-   const size_t n = (size_t)mParams.particle_count;
-   mGridStart.resize((size_t)cells + 1);
-   mGridMembers.resize(n ? n : 1);
-   check(sphb200_download(mCtx, SPHB200_F_GRID_START, mGridStart.data(), sizeof(int) * ((size_t)cells + 1)),
-         "download grid start");
-   check(sphb200_download(mCtx, SPHB200_F_GRID_MEMBERS, mGridMembers.data(), sizeof(uint32_t) * n),
-         "download grid members");
    mGrid.resize((size_t)cells);
+#ifdef SPHB200_WITH_QT
+   const bool members = true;
+#else
+   const bool members = mGridMembership;
+#endif
+   if (members || mReadback != ReadbackPositions)
+   {
+      std::lock_guard<std::mutex> ctxLock(mCtxMutex);
+      const size_t n = (size_t)mParams.particle_count;
+      if (members)
+      {
+         mGridStart.resize((size_t)cells + 1);
+         mGridMembers.resize(n ? n : 1);
+         check(sphb200_download(mCtx, SPHB200_F_GRID_START, mGridStart.data(), sizeof(int) * ((size_t)cells + 1)),
+               "download grid start");
+         check(sphb200_download(mCtx, SPHB200_F_GRID_MEMBERS, mGridMembers.data(), sizeof(uint32_t) * n),
+               "download grid members");
+      }
+      else
+      {
+         mGridCounts.resize((size_t)cells);
+         check(sphb200_download(mCtx, SPHB200_F_CELL_COUNT, mGridCounts.data(), sizeof(int) * (size_t)cells),
+               "download cell counts");
+      }
+   }
+   else if (!pullSnapshot(false, true) && mGridHave >= 0)
+      return mGrid.data();          // nothing newer than what the lists already show
    for (int c = 0; c < cells; c++)
    {
 #ifdef SPHB200_WITH_QT
@@ -238,7 +337,10 @@ SphCellList* SPH::getGrid()
       for (int k = mGridStart[c]; k < mGridStart[c + 1]; k++)
          mGrid[c].push_back(mGridMembers[k]);
 #else
-      mGrid[c].assign(mGridMembers.data() + mGridStart[c], mGridStart[c + 1] - mGridStart[c]);
+      if (members)
+         mGrid[c].assign(mGridMembers.data() + mGridStart[c], mGridStart[c + 1] - mGridStart[c]);
+      else
+         mGrid[c].assign(nullptr, (size_t)c < mGridCounts.size() ? mGridCounts[c] : 0);
 #endif
    }
    return mGrid.data();
@@ -246,6 +348,7 @@ SphCellList* SPH::getGrid()
 
 void SPH::pushParams()
 {
+   std::lock_guard<std::mutex> ctxLock(mCtxMutex);
    check(sphb200_set_params(mCtx, &mParams), "sphb200_set_params");
    check(sphb200_get_derived(mCtx, &mDerived), "sphb200_get_derived");
 }
@@ -257,8 +360,14 @@ void SPH::setGravity(const vec3& g)
    mParams.gravity[0] = g.x;
    mParams.gravity[1] = g.y;
    mParams.gravity[2] = g.z;
+   // the reference stores mGravity and never reads it (sph.cpp:1225-1228); here a
+   // non-zero value makes the row live: a += g after the CFL clamp (zero = the reference)
+   mParams.use_uniform_gravity = (g.x != 0.0f || g.y != 0.0f || g.z != 0.0f) ? 1 : 0;
    pushParams();
 }
+
+void SPH::setUniformGravity(bool on) { mParams.use_uniform_gravity = on ? 1 : 0; pushParams(); }
+void SPH::setWallCollision(bool on) { mParams.use_wall_collision = on ? 1 : 0; pushParams(); }
 
 float SPH::getStiffness() const { return mParams.stiffness; }
 void SPH::setStiffness(float v) { mParams.stiffness = v; pushParams(); }
@@ -267,6 +376,15 @@ void SPH::setViscosityScalar(float v) { mParams.viscosity = v; pushParams(); }
 float SPH::getTimeStep() const { return mParams.time_step; }
 void SPH::setTimeStep(float v) { mParams.time_step = v; pushParams(); }
 float SPH::getDamping() const { return mParams.damping; }
-void SPH::setDamping(float v) { mParams.damping = v; pushParams(); }
+// mDamping only feeds handleBoundaryConditions, which the reference never calls (sph.cpp:
+// 1025-1148).  SphConfig::writeValuesToSimulation passes the unchanged default on
+// every Apply, so only a value the user actually edited switches the wall code on.
+void SPH::setDamping(float v)
+{
+   mParams.damping = v;
+   if (v != mDefaultDamping)
+      mParams.use_wall_collision = 1;
+   pushParams();
+}
 float SPH::getCflLimit() const { return mParams.cfl_limit; }
 void SPH::setCflLimit(float v) { mParams.cfl_limit = v; pushParams(); }   // cfl^2 is re-derived (sph.cpp:1237-1241)

@@ -108,3 +108,23 @@ def test_no_cpu_fallback():
     with pytest.raises(S.SphError) as e:
         S.SPH()
     assert "no CUDA device" in str(e.value) and e.value.code == -2
+
+
+def test_reference_gui_call_sites_compile_against_the_facade():
+    """SURVEY 8(f3) without Qt: tests/conformance/reference_callsites.cpp repeats every statement
+    with which main.cpp:20-69, visualization.cpp:144-157 / 175-193 / 327-335, sphconfig.cpp:56-95
+    and widget.cpp:108-125 touch `class SPH`; it must compile against host/sph.h as is."""
+    import subprocess
+    host = os.path.join(ROOT, "smoothed_particle_hydrodynamics_b200", "host")
+    r = subprocess.run(["g++", "-std=c++11", "-fsyntax-only", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        "-I", host, os.path.join(ROOT, "tests", "conformance", "reference_callsites.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # and the facade declares every public name of the reference's class (src/sph.h:20-84)
+    decl = open(os.path.join(host, "sph.h")).read()
+    for name in ("isStopped", "isPaused", "getParticles", "getParticleCount", "getGridCellCounts", "getParticleBounds",
+                 "getInteractionRadius2", "getGrid", "getCellSize", "getGravity", "setGravity", "getStiffness",
+                 "setStiffness", "getViscosityScalar", "setViscosityScalar", "getTimeStep", "setTimeStep", "getDamping",
+                 "setDamping", "getCflLimit", "setCflLimit", "run", "step", "pauseResume", "stopSimulation",
+                 "updateElapsed", "stepFinished"):
+        assert re.search(r"\b%s\b" % name, decl), name

@@ -43,3 +43,17 @@ def test_headless_run_writes_the_reference_logs(tmp_path, golden_default):
     avg, mx, mn = [int(x) for x in nb[0].split(",")]
     cnt = golden_default["nbr_count_1"].astype(np.int64)
     assert (avg, mx, mn) == (int(cnt.sum()) // cnt.size, int(cnt.max()), min(34, int(cnt.min())))
+
+
+def test_facade_readback_path():
+    """getGrid()[c].count() == CELL_COUNT for every voxel, the position mirror is
+    current after step(), step() with the throttled position readback costs < 1.2x a step without
+    (1 M particles), and the GUI's gravity row is live (host/facade_check.cpp prints the numbers)."""
+    exe = os.path.join(ROOT, "smoothed_particle_hydrodynamics_b200", "facade_check")
+    if not os.path.exists(exe):
+        pytest.fail("facade_check is not built (python -m smoothed_particle_hydrodynamics_b200.build)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    print(r.stdout)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for name in ("mirror_positions", "grid_counts", "grid_members", "readback_cost", "gravity_row_live"):
+        assert "PASS " + name in r.stdout, r.stdout

@@ -611,3 +611,43 @@ def test_sampled_examine_count_64_vs_oracle():
     assert np.array_equal(nb, onb) and np.array_equal(nd, ond)
     check_state(sph.download(F.POSITION), o.pos, 1.0)
     sph.close()
+
+
+@pytest.mark.parametrize("mode", ["sampled", "full"])
+def test_viewer_snapshots_and_step_report(mode):
+    """sphb200_snapshot_request / _read (the GL view's readback contract, visualization.cpp:137-213)
+    and sphb200_get_step_report: the snapshot of step s holds exactly the positions and per-voxel
+    counts a synchronous download returns after step s; a reader that already has it gets nothing
+    new; the report equals the individual scalar getters."""
+    if mode == "sampled":
+        sph = S.SPH()
+    else:
+        p, lat = S.scene_config("dambreak_128k")
+        sph = S.SPH(p, init_scene=False)
+        sph.upload(S.scene_generate(lat), np.zeros((p.particle_count, 3), np.float32))
+    have, pos, cnt = sph.snapshot_read(cell_counts=True)
+    assert have == -1                                       # nothing requested yet
+    for s in range(1, 4):
+        sph.step_n(1)
+        sph.snapshot_request(positions=True, cell_counts=True)
+        ref_pos = sph.download(F.POSITION)
+        ref_cnt = sph.download(F.CELL_COUNT)
+        got, pos, cnt = sph.snapshot_read(have=have, wait=True, cell_counts=True)
+        assert got == s and got > have
+        assert np.array_equal(pos, ref_pos) and np.array_equal(cnt, ref_cnt)
+        assert cnt.sum() == sph.params.particle_count
+        have = got
+        again, _, _ = sph.snapshot_read(have=have, wait=True, cell_counts=True)
+        assert again == have
+    # steps keep running while a snapshot is on the wire; the snapshot still shows ITS step
+    sph.snapshot_request(positions=True, cell_counts=False)
+    before = sph.download(F.POSITION)
+    sph.step_n(3)
+    got, pos, _ = sph.snapshot_read(have=-1, wait=True)
+    assert got == 3 and np.array_equal(pos, before)
+    rep = sph.step_report()
+    ek, ep = sph.energies()
+    tot, mx, mn = sph.neighbor_stats()
+    assert (rep.e_kin, rep.e_pot, rep.nbr_total, rep.nbr_max, rep.nbr_min) == (ek, ep, tot, mx, mn)
+    assert rep.step_index == 6
+    sph.close()
