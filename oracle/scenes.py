@@ -55,6 +55,8 @@ def lattice_scene(nx, ny, nz, spacing, origin=(0.0, 0.0, 0.0), seed=42, first_id
 CONFIGS = {
     "dambreak_1m": dict(sites=(128, 64, 128), grid=(80, 32, 32), origin_vox=(0, 0, 0)),
     "dambreak_16m": dict(sites=(256, 128, 512), grid=(160, 64, 128), origin_vox=(0, 0, 0)),
+    # a quarter of the 16M block in z: the reference arm's sample when 16M would not end in minutes
+    "dambreak_4m": dict(sites=(256, 128, 128), grid=(160, 64, 32), origin_vox=(0, 0, 0)),
     # per-GPU slab of the 128M box-drop: lifted 16 voxels, centred in x
     "boxdrop_16m": dict(sites=(256, 128, 512), grid=(160, 64, 128), origin_vox=(49, 16, 3)),
     # small cases for parity tests

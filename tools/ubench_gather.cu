@@ -68,6 +68,39 @@ __global__ void __launch_bounds__(128, 4) k_gather(const float4* __restrict__ a,
       out[k] = acc;
 }
 
+// the same trips with the position record staged in shared memory (LDS.128 at a random slot of a
+// 2048-slot window, 32 KB per CTA -> 6 CTAs per SM) and the velocity record through MODE:
+//   0: TEX   1: LDG   2: a second LDS.128   3: nothing (LDS only)
+template <int MODE>
+__global__ void __launch_bounds__(128, 6) k_gather_smem(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                        cudaTextureObject_t tb, int n, float4* __restrict__ out)
+{
+   extern __shared__ float4 tile[];
+   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+   for (int i = threadIdx.x; i < 2048; i += blockDim.x)
+      tile[i] = a[(blockIdx.x * 128 + i) % n];
+   __syncthreads();
+   const int base = (k & ~31) + 16;
+   uint32_t s = (uint32_t)k * 2654435761u + 12345u;
+   float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll 1
+   for (int t = 0; t < TRIPS; t += 2)
+   {
+      int j0 = pick(s, base, n), j1 = pick(s, base, n);
+      float4 p0 = tile[j0 & 2047], p1 = tile[j1 & 2047], v0, v1;
+      if (MODE == 0) { v0 = tex1Dfetch<float4>(tb, j0); v1 = tex1Dfetch<float4>(tb, j1); }
+      else if (MODE == 1) { v0 = __ldg(&b[j0]); v1 = __ldg(&b[j1]); }
+      else if (MODE == 2) { v0 = tile[(j0 * 7 + 3) & 2047]; v1 = tile[(j1 * 7 + 3) & 2047]; }
+      else { v0 = make_float4(1, 1, 1, 1); v1 = v0; }
+      acc.x += p0.x * v0.x + p1.x * v1.x;
+      acc.y += p0.y * v0.y + p1.y * v1.y;
+      acc.z += p0.z * v0.z + p1.z * v1.z;
+      acc.w += p0.w * v0.w + p1.w * v1.w;
+   }
+   if (k < n)
+      out[k] = acc;
+}
+
 // LDS.128 at lane-dependent slots of a staged tile (SLOTS records of 16 B)
 template <int RANDOM>
 __global__ void __launch_bounds__(512, 1) k_lds(float4* out, long long* cyc, int slots)
@@ -142,6 +175,23 @@ int main()
          if (rep)
             printf("gather %-8s : %.3f ms for %d targets x %d trips x 2 records (%.1f clk per warp-trip and SM at 1.965 GHz)\n",
                    names[mode], ms, n, TRIPS, ms * 1e-3 * 1.965e9 * 148.0 / ((double)n / 32 * TRIPS));
+      }
+   const char* snames[4] = {"lds+tex", "lds+ldg", "lds+lds", "lds only"};
+   for (int rep = 0; rep < 2; rep++)
+      for (int mode = 0; mode < 4; mode++)
+      {
+         CK(cudaEventRecord(e0));
+         if (mode == 0) k_gather_smem<0><<<n / 128, 128, 32768>>>(a, b, tb, n, out);
+         if (mode == 1) k_gather_smem<1><<<n / 128, 128, 32768>>>(a, b, tb, n, out);
+         if (mode == 2) k_gather_smem<2><<<n / 128, 128, 32768>>>(a, b, tb, n, out);
+         if (mode == 3) k_gather_smem<3><<<n / 128, 128, 32768>>>(a, b, tb, n, out);
+         CK(cudaEventRecord(e1));
+         CK(cudaEventSynchronize(e1));
+         float ms = 0;
+         CK(cudaEventElapsedTime(&ms, e0, e1));
+         if (rep)
+            printf("gather %-8s : %.3f ms (%.1f clk per warp-trip and SM; includes staging 2048 slots per CTA)\n",
+                   snames[mode], ms, ms * 1e-3 * 1.965e9 * 148.0 / ((double)n / 32 * TRIPS));
       }
    long long* cyc;
    CK(cudaMalloc(&cyc, sizeof(long long) * 148));
