@@ -65,6 +65,10 @@ namespace
 #ifndef SPH_CAP
 #define SPH_CAP 6600
 #endif
+#ifndef SPH_DENS_PAIR
+#define SPH_DENS_PAIR 0          // 1: a thread of the density sweep owns TWO targets of one cell (register blocking:
+                                 // every candidate group is loaded once for both, all run / chunk bookkeeping is shared)
+#endif
 constexpr int kDensUnroll = SPH_DENS_UNROLL;
 constexpr int TBX = 8, TBY = SPH_TBY, TBZ = SPH_TBZ;   // tile extent in fine cells (x rows are contiguous in memory)
 constexpr int HROWS = (TBY + 2) * (TBZ + 2);   // halo rows (y,z) of a full tile
@@ -74,6 +78,9 @@ constexpr int kTileThreads = SPH_TILE_THREADS;
 constexpr int kTileCtas = SPH_TILE_CTAS;    // resident CTAs per SM the kernel is built for
 constexpr int kCap = SPH_CAP;               // staged particles per (sub-)tile, equal masses (12 B each)
 constexpr int kCapMass = (12 * (kCap + 4)) / 16 - 4;   // ... with per-particle masses (16 B each): same bytes
+constexpr int kPairCap = (kCap + TBX * TBY * TBZ) / 2 + 1;   // pairs of a staged tile: sum over cells of ceil(count / 2)
+static_assert(kCap < 32768, "a pair's first target number has 15 bits");
+static_assert(TBX * TBY * TBZ <= kTileThreads, "one thread per target cell builds the pair table");
 constexpr int WCAP = 32;                    // hit-mask records per particle (32 candidates each)
 constexpr unsigned kNoStream = 0xffu;       // info.nw value: no stream, scan instead
 #ifndef SPH_FORCE_RSM
@@ -108,7 +115,14 @@ struct TileLayout
    int total;                // staged particles
    int ntargets;
    int rowk[TROWS];          // sorted index of target t of row r = rowk[r] + t
+#if SPH_DENS_PAIR
+   int npairs;               // work items of the packed sweep: one or two targets of one cell
+   int wsum[32];
+   unsigned short pcode[kPairCap];   // per pair: lx | r << 4 | hr0 << 9  (its cell)
+   unsigned short ptgt[kPairCap];    // per pair: tile-local number of its first target | (two targets) << 15
+#else
    unsigned short tcell[kCap];   // per target: lx | r << 4 | hr0 << 9  (its cell; see locate_target)
+#endif
 };
 
 // ---- pair arithmetic ---------------------------------------------------------
@@ -504,6 +518,51 @@ __device__ void setup_layout(const DevParams& P, const SubTile& t, const uint32_
       }
    }
    __syncthreads();
+#if SPH_DENS_PAIR
+   // pair table (staged tiles hold at most kCap particles): one thread per target cell;
+   // a cell with c particles makes ceil(c / 2) work items, numbered by a block-wide scan
+   {
+      const int trows = t.by * t.bz;
+      const int ncell = trows * t.bx;
+      const int c = threadIdx.x;
+      int pc = 0, t0 = 0, cnt = 0;
+      unsigned short code = 0;
+      if (staged && c < ncell)
+      {
+         int r = c / t.bx, x = c - r * t.bx + 1;
+         int hr0 = (r / t.by + 1) * (t.by + 2) + (r % t.by + 1);
+         int first = L.cs[hr0][1];
+         t0 = L.tgt_off[r] + (L.cs[hr0][x] - first);
+         cnt = L.cs[hr0][x + 1] - L.cs[hr0][x];
+         code = (unsigned short)(x | (r << 4) | (hr0 << 9));
+         pc = (cnt + 1) >> 1;
+         if (x == 1)
+            L.rowk[r] = first - L.tgt_off[r];
+      }
+      int incl = pc;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1)
+      {
+         int up = __shfl_up_sync(0xffffffffu, incl, o);
+         if ((threadIdx.x & 31) >= o)
+            incl += up;
+      }
+      if ((threadIdx.x & 31) == 31)
+         L.wsum[threadIdx.x >> 5] = incl;
+      __syncthreads();
+      int base = incl - pc;
+      for (int w = 0; w < (int)(threadIdx.x >> 5); w++)
+         base += L.wsum[w];
+      for (int i = 0; i < pc; i++)
+      {
+         L.pcode[base + i] = code;
+         L.ptgt[base + i] = (unsigned short)((t0 + 2 * i) | ((2 * i + 1 < cnt) ? 0x8000 : 0));
+      }
+      if (threadIdx.x == blockDim.x - 1)
+         L.npairs = base + pc;
+   }
+   __syncthreads();
+#else
    // target -> cell table (staged tiles hold at most kCap particles): one thread per
    // target cell writes the code of its particles
    const int trows = t.by * t.bz;
@@ -521,6 +580,7 @@ __device__ void setup_layout(const DevParams& P, const SubTile& t, const uint32_
          L.rowk[r] = first - L.tgt_off[r];
    }
    __syncthreads();
+#endif
 }
 
 struct Target
@@ -549,6 +609,7 @@ __device__ __forceinline__ Target locate_target_search(const SubTile& t, const T
    return T;
 }
 
+#if !SPH_DENS_PAIR
 // maps flat target number -> particle and its cell (table built by setup_layout)
 __device__ __forceinline__ Target locate_target(const TileLayout& L, int tnum)
 {
@@ -559,6 +620,7 @@ __device__ __forceinline__ Target locate_target(const TileLayout& L, int tnum)
    T.k = L.rowk[(code >> 4) & 31u] + tnum;
    return T;
 }
+#endif
 
 // picks the sub-division level of this CTA's tile: 0 = whole tile ... 3 = every axis halved,
 // 4 = nothing fits (process from global memory).  Evaluated by warp 0.
@@ -800,6 +862,7 @@ __device__ __forceinline__ void density_group(unsigned a, f32x2 NX, f32x2 NY, f3
    }
 }
 
+#if !SPH_DENS_PAIR
 template <bool UNIT, bool UMASS>
 __device__ __forceinline__ void density_targets_packed(const DevParams& P, const SubTile& t, const TileLayout& L,
                                                        const float* __restrict__ sg,
@@ -901,6 +964,176 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
    }
 }
 
+#endif
+
+#if SPH_DENS_PAIR
+// one group of four candidates against TWO targets (a, b) of one cell: the three LDS.128 are
+// shared, the arithmetic of the two targets is independent (ILP 2)
+template <bool UNIT, bool UMASS, int OFF>
+__device__ __forceinline__ void density_group2(unsigned a, f32x2 NXa, f32x2 NYa, f32x2 NZa, f32x2 NXb, f32x2 NYb,
+                                               f32x2 NZb, f32x2 NH, f32x2 NTHR, f32x2 S2, unsigned& maska,
+                                               unsigned& maskb, f32x2& suma, f32x2& sumb)
+{
+   const ulonglong2 X = lds128<OFF>(a), Y = lds128<OFF + 16>(a), Z = lds128<OFF + 32>(a);
+   ulonglong2 M;
+   if (!UMASS)
+      M = lds128<OFF + 48>(a);
+#pragma unroll
+   for (int half = 0; half < 2; half++)
+   {
+      const f32x2 xs = half ? X.y : X.x, ys = half ? Y.y : Y.x, zs = half ? Z.y : Z.x;
+#pragma unroll
+      for (int tg = 0; tg < 2; tg++)
+      {
+         f32x2 dx = fadd2(xs, tg ? NXb : NXa);
+         f32x2 dy = fadd2(ys, tg ? NYb : NYa);
+         f32x2 dz = fadd2(zs, tg ? NZb : NZa);
+         f32x2 ee;
+         if (UNIT)
+            ee = ffma2(dz, dz, ffma2(dy, dy, ffma2(dx, dx, NH)));
+         else
+            ee = ffma2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))), S2, NH);
+         float s0, s1, e0, e1;
+         unpack2(fadd2(ee, NTHR), s0, s1);
+         unsigned& mask = tg ? maskb : maska;
+         mask = __funnelshift_l(__float_as_uint(s0), mask, 1);
+         mask = __funnelshift_l(__float_as_uint(s1), mask, 1);
+         unpack2(ee, e0, e1);
+         f32x2 u = pack2(fminf(e0, 0.0f), fminf(e1, 0.0f));
+         f32x2& acc = tg ? sumb : suma;
+         if (UMASS)
+            acc = ffma2(fmul2(u, u), u, acc);
+         else
+            acc = ffma2(fmul2(half ? M.y : M.x, u), fmul2(u, u), acc);
+      }
+   }
+}
+
+// The staged sweep with two targets per thread.  Work item = one or two consecutive targets of
+// ONE cell (pair table of setup_layout): they share the 9 runs, so every chunk / group is set up
+// and loaded once and evaluated against both.  A single target is evaluated twice (the second
+// result is dropped).
+template <bool UNIT, bool UMASS>
+__device__ __forceinline__ void density_pairs_packed(const DevParams& P, const SubTile& t, const TileLayout& L,
+                                                     const float* __restrict__ sg, const float4* __restrict__ s_pos4,
+                                                     const uint32_t* __restrict__ idx_sorted,
+                                                     const float4* __restrict__ vel4, float4* __restrict__ s_posA4,
+                                                     float4* __restrict__ s_velB4, float* __restrict__ s_rho,
+                                                     uint2* __restrict__ hit_rec, unsigned* __restrict__ hit_info)
+{
+   constexpr int GF = UMASS ? 12 : 16;   // floats per group
+   const float scale2 = P.scale * P.scale;
+   const float thr = 1e-5f * P.hs2;
+   const f32x2 NH = pack2(-P.hs2, -P.hs2), NTHR = pack2(-thr, -thr), S2 = pack2(scale2, scale2);
+   const unsigned sbase = (unsigned)__cvta_generic_to_shared(sg);
+   const int rowstep = t.by + 2;
+   for (int pn = threadIdx.x; pn < L.npairs; pn += blockDim.x)
+   {
+      const unsigned code = L.pcode[pn], tg = L.ptgt[pn];
+      const int lx = (int)(code & 15u), hr0 = (int)(code >> 9);
+      const bool two = (tg & 0x8000u) != 0u;
+      const int ka = L.rowk[(code >> 4) & 31u] + (int)(tg & 0x7fffu);
+      const int kb = two ? ka + 1 : ka;
+      const float4 pa = __ldg(&s_pos4[ka]), pb = __ldg(&s_pos4[kb]);
+      const f32x2 NXa = pack2(-pa.x, -pa.x), NYa = pack2(-pa.y, -pa.y), NZa = pack2(-pa.z, -pa.z);
+      const f32x2 NXb = pack2(-pb.x, -pb.x), NYb = pack2(-pb.y, -pb.y), NZb = pack2(-pb.z, -pb.z);
+      uint2* reca = hit_rec + stream_base(ka);
+      uint2* recb = hit_rec + stream_base(kb);
+      f32x2 suma = pack2(0.0f, 0.0f), sumb = pack2(0.0f, 0.0f);
+      int nwa = 0, nwb = 0, nhita = 0, nhitb = 0;
+      // the 9 runs in ascending row order: (z-1: y-1, y, y+1), (z: ...), (z+1: ...)
+      const int* csp = &L.cs[hr0 - rowstep - 1][lx - 1];
+      const int* dlp = &L.row_delta[hr0 - rowstep - 1];
+#pragma unroll kDensUnroll
+      for (int r = 0; r < 9; r++)
+      {
+         const int delta = dlp[0];
+         const int b = csp[0] + delta;
+         const int e = csp[3] + delta;
+         const bool last_of_plane = (r == 2 || r == 5);
+         csp += last_of_plane ? (rowstep - 2) * CSW : CSW;
+         dlp += last_of_plane ? rowstep - 2 : 1;
+#pragma unroll 1
+         for (int c0 = b & ~3; c0 < e; c0 += 32)
+         {
+            const int ng = min(8, (e - c0 + 3) >> 2);
+            const unsigned a0 = sbase + (unsigned)((c0 >> 2) * (GF * 4));   // the chunk's first group
+            unsigned maska = 0, maskb = 0;
+#define SPH_GROUP(N)                                                                                               \
+   density_group2<UNIT, UMASS, (N) * GF * 4>(a0, NXa, NYa, NZa, NXb, NYb, NZb, NH, NTHR, S2, maska, maskb, suma, sumb)
+            SPH_GROUP(0);
+            if (ng > 1)
+            {
+               SPH_GROUP(1);
+               if (ng > 2)
+               {
+                  SPH_GROUP(2);
+                  if (ng > 3)
+                  {
+                     SPH_GROUP(3);
+                     if (ng > 4)
+                     {
+                        SPH_GROUP(4);
+                        if (ng > 5)
+                        {
+                           SPH_GROUP(5);
+                           if (ng > 6)
+                           {
+                              SPH_GROUP(6);
+                              if (ng > 7)
+                                 SPH_GROUP(7);
+                           }
+                        }
+                     }
+                  }
+               }
+            }
+#undef SPH_GROUP
+            // keep the candidates of the run proper, [b, e) (see density_targets_packed)
+            const unsigned keep = (0xffffffffu >> max(b - c0, 0)) & __funnelshift_rc(0u, 0xffffffffu, e - c0);
+            const int sh = 32 - 4 * ng;
+            maska = (maska << sh) & keep;
+            maskb = (maskb << sh) & keep;
+            const unsigned base = (unsigned)(c0 - delta) | ((unsigned)r << 28);
+            if (maska != 0u)
+            {
+               if (nwa < WCAP)
+                  SPH_ST_ONCE(&reca[(size_t)nwa * 32], make_uint2(maska, base));
+               nwa++;
+               nhita += __popc(maska);
+            }
+            if (maskb != 0u)
+            {
+               if (two && nwb < WCAP)
+                  SPH_ST_ONCE(&recb[(size_t)nwb * 32], make_uint2(maskb, base));
+               nwb++;
+               nhitb += __popc(maskb);
+            }
+         }
+      }
+#pragma unroll
+      for (int tgt = 0; tgt < 2; tgt++)
+      {
+         if (tgt && !two)
+            break;
+         const int k = tgt ? kb : ka;
+         const float4 pi = tgt ? pb : pa;
+         const int nw = tgt ? nwb : nwa, nhits = tgt ? nhitb : nhita;
+         SPH_ST_ONCE(&hit_info[k], nw <= WCAP ? ((unsigned)nw | ((unsigned)nhits << 8)) : kNoStream);
+         float sa, sb;
+         unpack2(tgt ? sumb : suma, sa, sb);
+         const float sum = -(sa + sb);
+         // the particle itself sat in the centre run with e = -hs2: remove its own term (the
+         // reference skips realIndex == particleIndex, sph.cpp:737); a NaN position has term 0
+         float t_self = (pi.x == pi.x && pi.y == pi.y && pi.z == pi.z) ? P.hs2 : 0.0f;
+         float self = UMASS ? (t_self * t_self) * t_self : __fmul_rn(pi.w * t_self, t_self * t_self);
+         float rho = UMASS ? (P.k1 * pi.w) * (sum - self) : P.k1 * (sum - self);
+         density_store(P, k, pi, rho, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
+      }
+   }
+}
+#endif
+
 template <bool UNIT, bool UMASS>
 __global__ void __launch_bounds__(kTileThreads, kTileCtas)
    k_density_tiled(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ cell_start,
@@ -943,8 +1176,13 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtas)
                {
                   stage_rows_packed<UMASS>(t, L, s_pos4, sg);
                   __syncthreads();
+#if SPH_DENS_PAIR
+                  density_pairs_packed<UNIT, UMASS>(P, t, L, sg, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho,
+                                                    hit_rec, hit_info);
+#else
                   density_targets_packed<UNIT, UMASS>(P, t, L, sg, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho,
                                                       hit_rec, hit_info);
+#endif
                }
                else
                   density_targets<false, UNIT, UMASS>(P, t, L, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho,

@@ -68,6 +68,55 @@ __global__ void __launch_bounds__(128, 4) k_gather(const float4* __restrict__ a,
       out[k] = acc;
 }
 
+// a pick closer to the sweep's real pattern (~13 distinct lines per warp-wide load): all lanes are within
+// one row of a common row that advances with the trip
+__device__ __forceinline__ int pick_near(uint32_t& s, int base, int n, int t)
+{
+   uint32_t r = lcg(s);
+   int row = t * 9 / TRIPS + (int)(r % 3u) - 1;
+   row = row < 0 ? 0 : (row > 8 ? 8 : row);
+   int off = (int)((r >> 4) % (uint32_t)WIN);
+   int j = base + (row / 3 - 1) * PLANE + (row % 3 - 1) * ROW + off - WIN / 2;
+   j = j < 0 ? j + n : j;
+   return j >= n ? j - n : j;
+}
+
+struct __align__(32) Rec32 { float4 p, v; };
+
+// MODE 0: two LDG.128 from two arrays, 1: one 256-bit load from 32-byte records, 2: two LDG.128 from the
+// two halves of the 32-byte record (same line)
+template <int MODE>
+__global__ void __launch_bounds__(128, 4) k_gather_near(const float4* __restrict__ a, const float4* __restrict__ b,
+                                                        const Rec32* __restrict__ ab, int n, float4* __restrict__ out)
+{
+   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+   const int base = (k & ~31) + 16;
+   uint32_t s = (uint32_t)k * 2654435761u + 12345u;
+   float4 acc = make_float4(0, 0, 0, 0);
+#pragma unroll 1
+   for (int t = 0; t < TRIPS; t += 2)
+   {
+      int j0 = pick_near(s, base, n, t), j1 = pick_near(s, base, n, t + 1);
+      float4 p0, p1, v0, v1;
+      if (MODE == 0) { p0 = __ldg(&a[j0]); p1 = __ldg(&a[j1]); v0 = __ldg(&b[j0]); v1 = __ldg(&b[j1]); }
+      else if (MODE == 1)
+      {
+         float r0[8], r1[8];
+         asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(r0[0]), "=f"(r0[1]), "=f"(r0[2]), "=f"(r0[3]), "=f"(r0[4]), "=f"(r0[5]), "=f"(r0[6]), "=f"(r0[7]) : "l"(ab + j0));
+         asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" : "=f"(r1[0]), "=f"(r1[1]), "=f"(r1[2]), "=f"(r1[3]), "=f"(r1[4]), "=f"(r1[5]), "=f"(r1[6]), "=f"(r1[7]) : "l"(ab + j1));
+         p0 = make_float4(r0[0], r0[1], r0[2], r0[3]); v0 = make_float4(r0[4], r0[5], r0[6], r0[7]);
+         p1 = make_float4(r1[0], r1[1], r1[2], r1[3]); v1 = make_float4(r1[4], r1[5], r1[6], r1[7]);
+      }
+      else { p0 = __ldg(&ab[j0].p); v0 = __ldg(&ab[j0].v); p1 = __ldg(&ab[j1].p); v1 = __ldg(&ab[j1].v); }
+      acc.x += p0.x * v0.x + p1.x * v1.x;
+      acc.y += p0.y * v0.y + p1.y * v1.y;
+      acc.z += p0.z * v0.z + p1.z * v1.z;
+      acc.w += p0.w * v0.w + p1.w * v1.w;
+   }
+   if (k < n)
+      out[k] = acc;
+}
+
 // the same trips with the position record staged in shared memory (LDS.128 at a random slot of a
 // 2048-slot window, 32 KB per CTA -> 6 CTAs per SM) and the velocity record through MODE:
 //   0: TEX   1: LDG   2: a second LDS.128   3: nothing (LDS only)
@@ -175,6 +224,25 @@ int main()
          if (rep)
             printf("gather %-8s : %.3f ms for %d targets x %d trips x 2 records (%.1f clk per warp-trip and SM at 1.965 GHz)\n",
                    names[mode], ms, n, TRIPS, ms * 1e-3 * 1.965e9 * 148.0 / ((double)n / 32 * TRIPS));
+      }
+   Rec32* ab;
+   CK(cudaMalloc(&ab, sizeof(Rec32) * (size_t)n));
+   CK(cudaMemset(ab, 0, sizeof(Rec32) * (size_t)n));
+   const char* nnames[3] = {"near 2 x ldg128 (2 arrays)", "near 1 x ldg256 (32 B rec)", "near 2 x ldg128 (32 B rec)"};
+   for (int rep = 0; rep < 2; rep++)
+      for (int mode = 0; mode < 3; mode++)
+      {
+         CK(cudaEventRecord(e0));
+         if (mode == 0) k_gather_near<0><<<n / 128, 128>>>(a, b, ab, n, out);
+         if (mode == 1) k_gather_near<1><<<n / 128, 128>>>(a, b, ab, n, out);
+         if (mode == 2) k_gather_near<2><<<n / 128, 128>>>(a, b, ab, n, out);
+         CK(cudaEventRecord(e1));
+         CK(cudaEventSynchronize(e1));
+         float ms = 0;
+         CK(cudaEventElapsedTime(&ms, e0, e1));
+         if (rep)
+            printf("gather %-28s : %.3f ms (%.1f clk per warp-trip and SM)\n", nnames[mode], ms,
+                   ms * 1e-3 * 1.965e9 * 148.0 / ((double)n / 32 * TRIPS));
       }
    const char* snames[4] = {"lds+tex", "lds+ldg", "lds+lds", "lds only"};
    for (int rep = 0; rep < 2; rep++)
