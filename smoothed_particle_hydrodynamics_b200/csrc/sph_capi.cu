@@ -434,7 +434,7 @@ int sphb200_create(const SphParams* p, int device, sphb200_ctx** out)
          return rc;
    }
    ctx->partial_blocks = max_blocks;
-   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->d_block_partials, 2 * (size_t)max_blocks));
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->d_block_partials, 2 * (size_t)max_blocks + 2 * 256)   /* + second-stage partials */);
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->d_scalars, 1));
    SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->d_scalars, 0, sizeof(StepScalars), ctx->stream));
    for (int i = 0; i < 8; i++)

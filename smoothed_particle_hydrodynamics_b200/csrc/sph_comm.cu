@@ -147,9 +147,8 @@ __global__ void __launch_bounds__(kThreads)
    {
       p = pos4[i];
       v = vel4[i];
-      v.w = __uint_as_float(gid[i]);
    }
-   const unsigned char ns = sph_slab_emit(P, owned, p, v);
+   const unsigned char ns = sph_slab_emit(P, owned, p, v, (uint32_t)(valid ? i : 0));
    if (owned)
       st = ns == SLOT_LEAVING_GHOST ? (unsigned char)SLOT_GHOST : ns == SLOT_LEAVING_FREE ? (unsigned char)SLOT_FREE : st;
    else if (valid)

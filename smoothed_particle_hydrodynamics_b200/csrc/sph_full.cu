@@ -1343,9 +1343,7 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
             owned = true;
          }
       }
-      if (owned)
-         new_vel.w = __uint_as_float(P.slot_gid[o]);
-      const unsigned char st = sph_slab_emit(P, owned, new_pos, new_vel);
+      const unsigned char st = sph_slab_emit(P, owned, new_pos, new_vel, o);
       if (owned && st != SLOT_OWNED)
          P.slot_state[o] = st;
    }
@@ -1677,9 +1675,7 @@ __global__ void __launch_bounds__(kFThreads, SPH_FCTAS)
                owned = true;
             }
          }
-         if (owned)
-            new_vel.w = __uint_as_float(P.slot_gid[o]);
-         const unsigned char st = sph_slab_emit(P, owned, new_pos, new_vel);
+         const unsigned char st = sph_slab_emit(P, owned, new_pos, new_vel, o);
          if (owned && st != SLOT_OWNED)
             P.slot_state[o] = st;
       }

@@ -82,6 +82,7 @@ struct StepScalars     // per-step reductions, one device struct
    unsigned long long nbr_total;
    int nbr_max, nbr_min;
    int overflow;        // FULL list builder: count above capacity seen
+   unsigned finish_ticket;   // k_finish_scalars: blocks that have delivered their partial sum (self-resetting)
 };
 
 struct SlabComm;       // sph_comm.cu

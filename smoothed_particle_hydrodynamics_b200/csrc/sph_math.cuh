@@ -249,8 +249,11 @@ __device__ __forceinline__ unsigned sph_block_append(unsigned* counter, bool wan
 
 // Exchange rules for an OWNED particle at position z (sph_comm.cu header): appends it to
 // the outgoing messages as a migrant or as a boundary-layer ghost and returns the state
-// its slot takes.  All 32 lanes of the warp call this; `owned` selects the real ones.
-__device__ __forceinline__ unsigned char sph_slab_emit(const DevParams& P, bool owned, float4 pos, float4 vel_gid)
+// its slot takes.  All 32 lanes of the warp call this; `owned` selects the real ones.  `slot` is
+// the particle's slot: its global id (P.slot_gid, a scattered load) is fetched only for the few
+// particles that actually go into a message.
+__device__ __forceinline__ unsigned char sph_slab_emit(const DevParams& P, bool owned, float4 pos, float4 vel,
+                                                       uint32_t slot)
 {
    const int vz = sph_voxel_coord(pos.z, P.h_times2_inv, P.gz_global);
    // almost every warp is far from the slab faces: one vote instead of four appends
@@ -265,7 +268,9 @@ __device__ __forceinline__ unsigned char sph_slab_emit(const DevParams& P, bool 
    // go wherever the message lives -- in put mode that is the neighbour GPU's memory
    SlabEntry e;
    e.pos = pos;
-   e.vel = vel_gid;
+   e.vel = vel;
+   if (migrant || ghost_up || ghost_down)
+      e.vel.w = __uint_as_float(P.slot_gid[slot]);
    bool overflow = false;
    unsigned s = sph_warp_append(&P.send_cnt[2], mig_up);
    if (mig_up)
