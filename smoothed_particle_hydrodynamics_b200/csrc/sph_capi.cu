@@ -403,8 +403,11 @@ int sphb200_create(const SphParams* p, int device, sphb200_ctx** out)
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->keys_sorted, n));
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->idx_iota, n));
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->idx_sorted, n));
-   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->s_posA4, n));   // also the upload / download staging
-   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->s_velB4, n));
+   // the two force-sweep record arrays are ONE allocation (s_velB4 = s_posA4 + n rounded up to 32): the AoS build of the
+   // sweeps (SPH_FORCE_AOS) lays 32-byte records over it; also the upload / download staging
+   const size_t n_rec = (n + 31) & ~(size_t)31;   // 512-byte steps: the second array is also bound as a linear texture
+   SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->s_posA4, 2 * n_rec));
+   ctx->s_velB4 = ctx->s_posA4 + n_rec;
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->stage_f, n));
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->nbr_count, n));
    SPH_CUDA_CHECK(ctx, dev_alloc(&ctx->rho, n));
@@ -467,7 +470,7 @@ int sphb200_destroy(sphb200_ctx* ctx)
    if (ctx->tex_velB) cudaDestroyTextureObject(ctx->tex_velB);
    sph_grid_free(ctx);
    void* bufs[] = {ctx->pos4, ctx->vel4, ctx->gid, ctx->keys, ctx->keys_sorted, ctx->idx_iota, ctx->idx_sorted,
-                   ctx->slot_state, ctx->idx_fixed, ctx->s_pos4, ctx->s_posA4, ctx->s_velB4, ctx->s_rho,
+                   ctx->slot_state, ctx->idx_fixed, ctx->s_pos4, ctx->s_posA4, ctx->s_rho,
                    ctx->s_acc4, ctx->s_count, ctx->nbr_idx, ctx->nbr_dist, ctx->nbr_count, ctx->rho, ctx->acc4,
                    ctx->voxel_id, ctx->vg_count, ctx->vg_start, ctx->vg_members, ctx->vg_keys,
                    ctx->d_scalars, ctx->d_block_partials, ctx->stage_f, ctx->hit_rec, ctx->hit_info};

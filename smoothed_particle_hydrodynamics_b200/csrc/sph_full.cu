@@ -91,7 +91,10 @@ constexpr int RSM = SPH_FORCE_RSM;                     // records per thread kep
 #define SPH_FORCE_ILP 2
 #endif
 #ifndef SPH_FORCE_CTAS
-#define SPH_FORCE_CTAS 4
+#define SPH_FORCE_CTAS 10  // resident CTAs per SM the force sweep is built for: 10 -> 48 registers (18 values spilled), 40 warps
+                           // per SM.  With the velocity records on the texture path the sweep is latency bound (ncu r02:
+                           // long-scoreboard stall 5 warps per issue, LSU 62 %, TEX 43 %, issue 68 %): 4 / 8 (64 regs):
+                           // 2.31 ms, 9 / 10: 2.25 / 2.24, 12 (40 regs): 2.39; ILP 3 at 64 regs: 2.25, ILP 3 / 4 at 77 / 87: 2.75 / 3.14
 #endif
 constexpr int kForceIlp = SPH_FORCE_ILP;     // neighbours in flight per lane of the force sweep
 #ifndef SPH_FORCE_THREADS
@@ -104,6 +107,43 @@ constexpr int kForceThreads = SPH_FORCE_THREADS;
                            // stage with LDG -- tools/ubench_gather.cu -- but copes better with scattered lanes)
 #endif
 constexpr int kFlatThreads = 128;
+#ifndef SPH_FORCE_AOS
+#define SPH_FORCE_AOS 0    // 1: the force-sweep records are 32-byte structures {x,y,z,fA, vx,vy,vz,fB} fetched with one
+                           // 256-bit load per neighbour instead of two 128-bit loads from two arrays (A/B)
+#endif
+
+// force-sweep record access: two float4 arrays (A: x,y,z,fA  B: vx,vy,vz,fB), or -- SPH_FORCE_AOS -- one array
+// of 32-byte records laid over the same allocation (B follows A, sph_capi.cu)
+struct __align__(32) ForceRec
+{
+   float4 a, b;
+};
+
+__device__ __forceinline__ void rec_load(const float4* __restrict__ A, const float4* __restrict__ B, int j, float4& a,
+                                         float4& b)
+{
+#if SPH_FORCE_AOS
+   const ForceRec* r = reinterpret_cast<const ForceRec*>(A) + j;
+   asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                : "l"(r));
+#else
+   a = __ldg(&A[j]);
+   b = __ldg(&B[j]);
+#endif
+}
+
+__device__ __forceinline__ void rec_store(float4* __restrict__ A, float4* __restrict__ B, int k, float4 a, float4 b)
+{
+#if SPH_FORCE_AOS
+   ForceRec* r = reinterpret_cast<ForceRec*>(A) + k;
+   r->a = a;
+   r->b = b;
+#else
+   A[k] = a;
+   B[k] = b;
+#endif
+}
 
 struct TileLayout
 {
@@ -319,8 +359,7 @@ __device__ __forceinline__ void density_store(const DevParams& P, int k, float4 
    // step_host uploads the velocities while this sweep runs: then k_gather_vel fills them in
    float4 v = P.defer_velocity ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : __ldg(&vel4[idx_sorted[k]]);
    s_rho[k] = rho;
-   s_posA4[k] = make_float4(pi.x, pi.y, pi.z, fA);
-   s_velB4[k] = make_float4(v.x, v.y, v.z, fB);
+   rec_store(s_posA4, s_velB4, k, make_float4(pi.x, pi.y, pi.z, fA), make_float4(v.x, v.y, v.z, fB));
 }
 
 // force sweep epilogue: tail of computeAcceleration, integrate, walls, write-back
@@ -1230,8 +1269,8 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    int cmax = -1, cmin = 0x7fffffff;
    // per-particle operands and the records: independent loads, issued together
    const unsigned info = active ? SPH_LD_ONCE(&hit_info[kk]) : 0u;
-   const float4 pi = s_posA4[kk];
-   const float4 vi = s_velB4[kk];
+   float4 pi, vi;
+   rec_load(s_posA4, s_velB4, kk, pi, vi);
    const float rho_i = SPH_LD_ONCE(&s_rho[kk]);
    const bool scan = (info & 0xffu) == kNoStream;
    const int nw = scan ? 0 : (int)(info & 0xffu);
@@ -1289,8 +1328,16 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
 #pragma unroll
       for (int q = 0; q < kForceIlp; q++)
       {
-         pj[q] = (SPH_FORCE_TEX & 2) ? tex1Dfetch<float4>(tex_posA, j[q]) : __ldg(&s_posA4[j[q]]);
-         vj[q] = (SPH_FORCE_TEX & 1) ? tex1Dfetch<float4>(tex_velB, j[q]) : __ldg(&s_velB4[j[q]]);
+#if SPH_FORCE_AOS
+         rec_load(s_posA4, s_velB4, j[q], pj[q], vj[q]);
+#else
+         // SPH_FORCE_TEX 4: the two pipes share the work evenly -- even neighbours fetch (x, fA) through LSU and
+         // (v, fB) through TEX, odd neighbours the other way round
+         const bool swap = (SPH_FORCE_TEX & 4) && (q & 1);
+         const bool tex_p = swap ? true : (SPH_FORCE_TEX & 2) != 0, tex_v = swap ? false : (SPH_FORCE_TEX & 5) != 0;
+         pj[q] = tex_p ? tex1Dfetch<float4>(tex_posA, j[q]) : __ldg(&s_posA4[j[q]]);
+         vj[q] = tex_v ? tex1Dfetch<float4>(tex_velB, j[q]) : __ldg(&s_velB4[j[q]]);
+#endif
       }
       PairTerm t[kForceIlp];
 #pragma unroll
@@ -1307,7 +1354,11 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
 #pragma unroll 1
       for (int r = 0; r < 9; r++)
          for (int j = b[r]; j < e[r]; j++)
-            count += force_candidate<UNIT_SCALE>(P, I, __ldg(&s_posA4[j]), __ldg(&s_velB4[j]), j != k, pg, vt);
+         {
+            float4 pj, vj;
+            rec_load(s_posA4, s_velB4, j, pj, vj);
+            count += force_candidate<UNIT_SCALE>(P, I, pj, vj, j != k, pg, vt);
+         }
    }
    float4 new_pos = make_float4(0.0f, 0.0f, 0.0f, 0.0f), new_vel = new_pos;
    if (active)
@@ -1694,7 +1745,12 @@ __global__ void __launch_bounds__(kFlatThreads)
    if (k >= sph_live_count(P))
       return;
    float4 v = __ldg(&vel4[idx_sorted[k]]);
-   s_velB4[k] = make_float4(v.x, v.y, v.z, s_velB4[k].w);
+#if SPH_FORCE_AOS
+   float4* vb = &(reinterpret_cast<ForceRec*>(s_velB4)[k].b);   // the launcher passes the record base
+#else
+   float4* vb = &s_velB4[k];
+#endif
+   *vb = make_float4(v.x, v.y, v.z, vb->w);
 }
 
 // ---- on-demand outputs --------------------------------------------------------
@@ -1909,8 +1965,8 @@ int sph_step_full(sphb200_ctx* ctx)
       // sphb200_step_host: the velocity upload ran on a second stream beside binning and the
       // density sweep; join it here
       SPH_CUDA_CHECK(ctx, cudaStreamWaitEvent(st, ctx->deferred_vel_event, 0));
-      k_gather_vel<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, st>>>(P, ctx->idx_order, ctx->vel4,
-                                                                                  ctx->s_velB4);
+      k_gather_vel<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, st>>>(
+         P, ctx->idx_order, ctx->vel4, SPH_FORCE_AOS ? ctx->s_posA4 : ctx->s_velB4);
       ctx->launches++;
    }
    if (timed) cudaEventRecord(ctx->ev[4], st);
@@ -1918,7 +1974,7 @@ int sph_step_full(sphb200_ctx* ctx)
    // that stages the neighbour records in shared memory by TMA bulk copies (measured slower on
    // B200, profiles/r02_history.md: 5.09 vs 2.41 ms at 16.7M particles; kept for A/B)
    int blocks;
-   if (ctx->params.kernel_variant == 3)
+   if (ctx->params.kernel_variant == 3 && !SPH_FORCE_AOS)   // (the TMA-staged sweep copies rows of the two arrays)
    {
       dim3 ft((P.fx + FTX - 1) / FTX, (P.fy + FTY - 1) / FTY, (P.fz + FTZ - 1) / FTZ);
       blocks = (int)(ft.x * ft.y * ft.z);
