@@ -158,6 +158,19 @@ def column_scene(S, world, rank, strong, sites_xy=(256, 128), planes=512):
                 sites=(nx, ny, nz), params=p)
 
 
+def id_checksums(gids):
+    """(count, sum, xor) of a rank's owned global ids -- combined over ranks by sum / sum / xor."""
+    g = np.asarray(gids).astype(np.uint64)
+    return int(g.size), int(g.sum()), (int(np.bitwise_xor.reduce(g)) if g.size else 0)
+
+
+def id_checksums_ok(count, idsum, idxor, n_total):
+    """Every id 0 .. n_total-1 exactly once <=> (necessary) count, sum and xor equal their closed forms."""
+    xor_ref = [n_total - 1, 1, n_total, 0][(n_total - 1) % 4]
+    return {"owned_total": int(count), "expected": int(n_total), "id_sum_ok": idsum == n_total * (n_total - 1) // 2,
+            "id_xor_ok": idxor == xor_ref}
+
+
 class Dist:
     """torch.distributed plumbing (bootstrap, barriers, max / sum over ranks); a no-op for one rank."""
 
@@ -311,23 +324,22 @@ class Job:
         sph, D = self.sph, self.D
         sph.status()
         pos, gids = sph.download_slab(self.S.Field.POSITION)
-        g = gids.astype(np.uint64)
-        owned = D.sum(float(gids.size))
-        idsum = D.sum(float(g.sum()))
-        nt = self.n_total
-        x = int(np.bitwise_xor.reduce(g)) if g.size else 0
+        count, idsum, idxor = id_checksums(gids)
+        # (sums stay below 2^53: 134M ids sum to 9.0e15)
+        count, idsum = int(D.sum(float(count))), int(D.sum(float(idsum)))
         if D.dist:
-            t = self.torch.tensor([x], device="cuda", dtype=self.torch.int64)
+            t = self.torch.tensor([idxor], device="cuda", dtype=self.torch.int64)
             parts = [self.torch.zeros_like(t) for _ in range(self.world)]
             D.dist.all_gather(parts, t)
-            x = 0
+            idxor = 0
             for q in parts:
-                x ^= int(q.item())
-        xor_ref = [nt - 1, 1, nt, 0][(nt - 1) % 4]         # xor of 0 .. nt-1
-        finite = D.sum(float(np.isfinite(pos).all())) == self.world
-        ok = owned == nt and idsum == nt * (nt - 1) / 2 and x == xor_ref and finite
-        return {"owned_total": int(owned), "expected": nt, "id_sum_ok": idsum == nt * (nt - 1) / 2,
-                "id_xor_ok": x == xor_ref, "state_finite": bool(finite), "slab_status": "ok", "ok": bool(ok)}
+                idxor ^= int(q.item())
+        out = id_checksums_ok(count, idsum, idxor, self.n_total)
+        out["state_finite"] = D.sum(float(np.isfinite(pos).all())) == self.world
+        out["slab_status"] = "ok"
+        out["ok"] = bool(out["owned_total"] == out["expected"] and out["id_sum_ok"] and out["id_xor_ok"]
+                         and out["state_finite"])
+        return out
 
     def e2e(self, steps):
         """End to end through host buffers: every step H2D of positions / velocities / masses (/ ids) from
@@ -371,7 +383,9 @@ def roofline_block(job, phase, clocks, hbm, peak_kind):
     the FP32 pipe (148 SMs x 128 lanes x 2 flop x clock) with the FP32 operation count of the committed
     ncu capture, and that capture's DRAM traffic."""
     dens_ms, force_ms = float(phase[2]), float(phase[4])
-    if force_ms >= dens_ms:
+    # the two sweeps take the same time to within run-to-run noise; a near-tie (3 %) goes to the force sweep, the
+    # one that carries more of the step's algorithmic bytes (both are listed under "sweeps")
+    if force_ms >= 0.97 * dens_ms:
         dom = {"key": "force", "ms": force_ms, "bytes": ALG_BYTES_FORCE, "bound": "l1",
                "kernel": "k_force_stream (pressure + viscosity + integrate + walls, hit-mask stream driven)",
                "note": "bound by the L1 data pipe: two scattered 16-byte neighbour gathers per pair, ~13 distinct "
@@ -396,7 +410,12 @@ def roofline_block(job, phase, clocks, hbm, peak_kind):
                 "issue_active_pct_ncu": km.get("issue_pct"), "dram_pct_ncu": km.get("dram_pct"),
                 "inst_executed_ncu": km.get("inst_executed"), "ncu_kernel_ms": km["ncu_ms"],
                 "peak_formula": "148 SMs x 128 lanes x 2 flop x %.0f MHz" % (clk / 1e6)}
-    return {"bound": dom["bound"], "contract_bound": "hbm", "kernel": dom["kernel"],
+    sweeps = [{"kernel": name, "kernel_ms": ms, "alg_bytes_per_particle": b, "achieved": b * job.n / (ms * 1e-3) / 1e9,
+               "frac": b * job.n / (ms * 1e-3) / 1e9 / hbm}
+              for name, ms, b in (("k_density_tiled", dens_ms, ALG_BYTES_DENSITY), ("k_force_stream", force_ms, ALG_BYTES_FORCE),
+                                  ("k_cell_keys + scan + k_scatter + k_rank_gather", float(phase[0]),
+                                   ALG_BYTES_STEP - ALG_BYTES_DENSITY - ALG_BYTES_FORCE)) if ms > 0]
+    return {"bound": dom["bound"], "contract_bound": "hbm", "kernel": dom["kernel"], "sweeps": sweeps,
             "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm,
             "traffic": km["dram_bytes"] if km else None,
             "traffic_unit": "bytes per launch: ncu dram__bytes_read.sum + dram__bytes_write.sum (%s)"

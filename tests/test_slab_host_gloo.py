@@ -29,7 +29,21 @@ def _worker(rank, world, port, q):
     if rank == 0:
         idt.copy_(torch.arange(128, dtype=torch.uint8))
     dist.broadcast(idt, 0)
-    sc = bench.column_scene(world, rank, True, sites_xy=(32, 16), planes=64)
+    import smoothed_particle_hydrodynamics_b200 as S
+    sc = bench.column_scene(S, world, rank, True, sites_xy=(32, 16), planes=64)
+    # the integrity record of bench.py's slab lines: count / sum / xor of the owned ids over all ranks
+    cnt, idsum, idxor = bench.id_checksums(sc["gids"])
+    red = torch.tensor([cnt, idsum], dtype=torch.int64)
+    dist.all_reduce(red)
+    xors = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(xors, torch.tensor([idxor], dtype=torch.int64))
+    x = 0
+    for t in xors:
+        x ^= int(t.item())
+    ok = bench.id_checksums_ok(int(red[0]), int(red[1]), x, sc["total"])
+    assert ok["owned_total"] == ok["expected"] and ok["id_sum_ok"] and ok["id_xor_ok"], ok
+    bad = bench.id_checksums_ok(int(red[0]), int(red[1]) + 1, x, sc["total"])       # one id off: caught
+    assert not bad["id_sum_ok"]
     n_local = torch.tensor([sc["gids"].size], dtype=torch.int64)
     dist.all_reduce(n_local)
     gz = torch.tensor([sc["grid"][2]], dtype=torch.int64)
@@ -61,7 +75,7 @@ def test_two_ranks_partition_and_bootstrap():
     # each rank's particles are the global scene's particles with those ids
     from oracle import scenes
     d = scenes.lattice_spacing(0.1, 40.0)
-    glob = scenes.lattice_scene(32, 16, 64, d, origin=(49 * 0.2, 16 * 0.2, 3 * 0.2))
+    glob = scenes.lattice_scene(32, 16, 64, d, origin=(np.float32(49 * 0.2), np.float32(16 * 0.2), 3 * 0.2))
     assert np.array_equal(glob[g0], p0) and np.array_equal(glob[g1], p1)
     # and they lie in the voxel layers the rank owns
     inv2h = np.float32(1.0) / (np.float32(0.1) * np.float32(2.0))
