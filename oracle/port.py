@@ -52,7 +52,8 @@ def lib():
         build()
         _lib = C.CDLL(LIB)
         for f in ("oracle_default_params", "oracle_derive", "oracle_init_sphere", "oracle_voxelize",
-                  "oracle_build_lists", "oracle_find_sampled", "oracle_fine_keys", "oracle_find_full",
+                  "oracle_build_lists", "oracle_order_cells_by_x", "oracle_find_sampled", "oracle_fine_keys",
+                  "oracle_find_full",
                   "oracle_density", "oracle_acceleration", "oracle_integrate"):
             getattr(_lib, f).restype = None
     return _lib
@@ -140,6 +141,7 @@ class OracleSPH:
             self.fstart = np.empty(fcells + 1, np.int32)
             self.fmembers = np.empty(n, np.uint32)
             self.lib.oracle_build_lists(n, fcells, _p(self.fine_keys), _p(self.fstart), _p(self.fmembers))
+            self.lib.oracle_order_cells_by_x(fcells, _p(self.fstart), _p(self.fmembers), _p(self.pos))
             self.lib.oracle_find_full(C.byref(p), _p(self.pos), _p(self.fine_xyz), _p(self.fstart),
                                       _p(self.fmembers), _p(self.nbr), _p(self.dist), _p(self.count))
             if int(self.count.max(initial=0)) > E:

@@ -210,7 +210,7 @@ struct Probe : public SPH
    // around the particle's fine cell, which all lie inside the 2x2x2 voxel
    // octant that findNeighbors picks (sph.cpp:504-556).  Test and stored
    // distance are the reference's (sph.cpp:633-641, 653, 668): d2 < mH2,
-   // sqrtf(d2) * scale.  Order: ascending (fine key, particle index).
+   // sqrtf(d2) * scale.  Order: ascending (fine key, x, particle index).
    // Returns the largest count; counts above capacity are truncated (the
    // return value tells the caller to enlarge examine_count).
    int phaseFindFull()
@@ -241,6 +241,22 @@ struct Probe : public SPH
          std::vector<uint32_t> fill(start.begin(), start.end() - 1);
          for (int i = 0; i < n; i++)          // ascending i inside each cell
             members[fill[fineKey[i]]++] = (uint32_t)i;
+      }
+      // ... then ascending (x, i) inside each cell: x through the order-preserving map of the float bits
+      // (FULL-mode canonical order; makes every x-run ascending in x)
+      {
+         const float* P = mSrcParticles->mPosition.data();
+         auto key = [P](uint32_t q) -> uint32_t {
+            uint32_t b;
+            const float x = P[(size_t)q * 3];
+            if (x != x)
+               return 0u;                       // NaN first
+            memcpy(&b, &x, sizeof b);
+            return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+         };
+         for (size_t c = 0; c < cells; c++)
+            std::stable_sort(members.begin() + start[c], members.begin() + start[c + 1],
+                             [&key](uint32_t a, uint32_t b) -> bool { return key(a) < key(b); });
       }
       long long total = 0;
       int mx = -1, mn = 0x7fffffff;

@@ -173,6 +173,38 @@ void oracle_build_lists(int n, int cells, const int* keys, int* start, uint32_t*
    free(fill);
 }
 
+/* FULL mode only (A.8): inside every fine cell the members are ordered by ascending
+ * (x, particle index) -- x compared through the usual order-preserving map of the float
+ * bits to unsigned (-0 < +0); a NaN (which is binned into cell 0 of its row) comes first.  Together with the cell
+ * order (x fastest) this makes every x-run of three cells ascending in x, which is what
+ * lets the CUDA sweeps cut a run down to |dx| < h before testing candidates.  The
+ * reference has no FULL mode; its sampled mode keeps the push_back order (ascending index). */
+static uint32_t x_order_key(float x)
+{
+   uint32_t b;
+   if (x != x)
+      return 0u;
+   memcpy(&b, &x, sizeof b);
+   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+void oracle_order_cells_by_x(int cells, const int* start, uint32_t* members, const float* pos)
+{
+   for (int c = 0; c < cells; c++)
+      for (int a = start[c] + 1; a < start[c + 1]; a++)       /* stable insertion sort: ties keep ascending index */
+      {
+         uint32_t q = members[a];
+         uint32_t kq = x_order_key(pos[3 * (size_t)q]);
+         int b = a - 1;
+         while (b >= start[c] && x_order_key(pos[3 * (size_t)members[b]]) > kq)
+         {
+            members[b + 1] = members[b];
+            b--;
+         }
+         members[b + 1] = q;
+      }
+}
+
 /* orientation inside the voxel and the octant direction, sph.cpp:504-515 */
 static void octant_signs(const OracleParams* p, const float* pos_i, const int* v, int* s)
 {
@@ -273,7 +305,8 @@ void oracle_find_sampled(const OracleParams* p, const float* pos, const int* vox
  * Fine cell (edge h) = 2*voxel + (orientation > h) per axis, with the
  * reference's voxel (A.1) and orientation (sph.cpp:504-515).  Neighbours of i
  * = every j != i in the 27 fine cells around i with d2 < h2 (test and stored
- * distance as sph.cpp:633-641, 653, 668).  Order: ascending (fine key, j).
+ * distance as sph.cpp:633-641, 653, 668).  Order: ascending (fine key, x_j, j) -- the
+ * member order oracle_order_cells_by_x leaves in fmembers.
  * count[i] is the true count; only the first E are stored. */
 void oracle_fine_keys(const OracleParams* p, const float* pos, const int* voxel_xyz,
                       int* fine_xyz, int* fine_keys)

@@ -923,7 +923,13 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
       const float4 pi = __ldg(&s_pos4[T.k]);
       const f32x2 NX = pack2(-pi.x, -pi.x), NY = pack2(-pi.y, -pi.y), NZ = pack2(-pi.z, -pi.z);
       uint2* rec = hit_rec + stream_base(T.k);
-      f32x2 sum2 = pack2(0.0f, 0.0f), sum2b = pack2(0.0f, 0.0f);
+      // Every run sums into its own pair of accumulators (alternate candidates) that is folded into
+      // the total when the run ends: a run's contribution then does not depend on where in shared
+      // memory the run starts (a shift by one slot only swaps the two accumulators), so particles
+      // in front of a run that are nobody's neighbour -- NaN positions parked in cell 0 of a row,
+      // e.g. in transit through a slab -- cannot change any sum.
+      float total = 0.0f;
+      f32x2 sum2b = pack2(0.0f, 0.0f);
       int nw = 0, nhits = 0;
       // the 9 runs in ascending row order: (z-1: y-1, y, y+1), (z: ...), (z+1: ...)
       const int* csp = &L.cs[T.hr0 - rowstep - 1][T.lx - 1];
@@ -931,6 +937,7 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
 #pragma unroll kDensUnroll
       for (int r = 0; r < 9; r++)
       {
+         f32x2 sum2 = pack2(0.0f, 0.0f);
          const int delta = dlp[0];
          const int b = csp[0] + delta;
          const int e = csp[3] + delta;
@@ -989,11 +996,14 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
                nhits += __popc(mask);
             }
          }
+         float ra, rb;
+         unpack2(sum2, ra, rb);
+         total += ra + rb;
       }
       SPH_ST_ONCE(&hit_info[T.k], nw <= WCAP ? ((unsigned)nw | ((unsigned)nhits << 8)) : kNoStream);
       float sa, sb;
-      unpack2(SPH_DENS_SPLIT_ACC ? fadd2(sum2, sum2b) : sum2, sa, sb);
-      const float sum = -(sa + sb);
+      unpack2(sum2b, sa, sb);
+      const float sum = -(total + (SPH_DENS_SPLIT_ACC ? sa + sb : 0.0f));
       // the particle itself sat in the centre run with e = -hs2: remove its own term (the
       // reference skips realIndex == particleIndex, sph.cpp:737); a NaN position has term 0
       float t_self = (pi.x == pi.x && pi.y == pi.y && pi.z == pi.z) ? P.hs2 : 0.0f;

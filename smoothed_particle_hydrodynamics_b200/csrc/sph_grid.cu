@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(DevParams P, int cells, 
                                                          uint32_t* __restrict__ keys,
                                                          uint32_t* __restrict__ cell_count,
                                                          uint32_t* __restrict__ cell_slot,
-                                                         int* __restrict__ voxel_id_out)
+                                                         int* __restrict__ voxel_id_out, uint32_t* __restrict__ xkey)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (P.slab)
@@ -70,20 +70,25 @@ __global__ void __launch_bounds__(kThreads) k_cell_keys(DevParams P, int cells, 
    else
       key = (uint32_t)sph_voxel_id(vx, vy, lz, P.gx, P.gy);
    keys[i] = key;
+   if (FINE)
+      xkey[i] = sph_x_order_key(p.x);
    if (voxel_id_out)
       voxel_id_out[i] = sph_voxel_id(vx, vy, vz, P.gx, P.gy);   // global voxel id, as the reference numbers it
    cell_slot[i] = atomicAdd(&cell_count[key], 1u);
 }
 
 // counting-sort scatter: particle i goes to position cell_start[key] + slot.  The
-// slot order inside a cell is whatever the atomics produced; `ord` carries the value
-// the members are ranked by afterwards (particle index, or global id in slab mode).
+// slot order inside a cell is whatever the atomics produced; `pair` carries the value
+// the members are ranked by afterwards: (x order key, id) as one 64-bit word -- id =
+// particle index, or global id in slab mode; the x key is 0 in sampled mode.
 __global__ void __launch_bounds__(kThreads) k_scatter(int n, const uint32_t* __restrict__ keys,
                                                        const uint32_t* __restrict__ cell_slot,
                                                        const uint32_t* __restrict__ cell_start,
                                                        const uint32_t* __restrict__ gid,
+                                                       const uint32_t* __restrict__ xkey,
                                                        uint32_t* __restrict__ keys_sorted,
-                                                       uint32_t* __restrict__ tmp_ord, uint32_t* __restrict__ tmp_idx)
+                                                       unsigned long long* __restrict__ pair,
+                                                       uint32_t* __restrict__ tmp_idx)
 {
    int i = blockIdx.x * blockDim.x + threadIdx.x;
    if (i >= n)
@@ -91,23 +96,27 @@ __global__ void __launch_bounds__(kThreads) k_scatter(int n, const uint32_t* __r
    uint32_t key = keys[i];
    uint32_t p = __ldg(&cell_start[key]) + cell_slot[i];
    keys_sorted[p] = key;
+   const unsigned long long hi = xkey ? (unsigned long long)xkey[i] << 32 : 0ull;
    if (gid)
    {
-      tmp_ord[p] = gid[i];
+      pair[p] = hi | gid[i];
       tmp_idx[p] = (uint32_t)i;
    }
    else
-      tmp_ord[p] = (uint32_t)i;
+      pair[p] = hi | (uint32_t)i;
 }
 
 // One thread per sorted position: rank of its particle among the members of its cell
 // (cells hold ~8 particles and the members sit in consecutive, L1-resident words), then
 // the final index order and -- FULL mode -- the position gathered into cell order.
+// Rank = ascending (x, id) in FULL mode (every x-run of the sweeps is then ascending in x;
+// oracle_order_cells_by_x), ascending id = the reference's push_back order in sampled mode
+// (sph.cpp:476-480): one 64-bit comparison either way.
 // Free slots (slab mode, sentinel cell `cells`) keep their arbitrary order.
 template <bool GATHER>
 __global__ void __launch_bounds__(kThreads) k_rank_gather(int n, int cells, const uint32_t* __restrict__ keys_sorted,
                                                            const uint32_t* __restrict__ cell_start,
-                                                           const uint32_t* __restrict__ tmp_ord,
+                                                           const unsigned long long* __restrict__ pair,
                                                            const uint32_t* __restrict__ tmp_idx,
                                                            const float4* __restrict__ pos4,
                                                            uint32_t* __restrict__ idx_sorted,
@@ -117,8 +126,8 @@ __global__ void __launch_bounds__(kThreads) k_rank_gather(int n, int cells, cons
    if (k >= n)
       return;
    const uint32_t c = keys_sorted[k];
-   const uint32_t mine = tmp_ord[k];
-   const uint32_t me = tmp_idx ? tmp_idx[k] : mine;
+   const unsigned long long mine = pair[k];
+   const uint32_t me = tmp_idx ? tmp_idx[k] : (uint32_t)mine;
    if ((int)c >= cells)
    {
       idx_sorted[k] = me;
@@ -127,7 +136,7 @@ __global__ void __launch_bounds__(kThreads) k_rank_gather(int n, int cells, cons
    const int s = (int)__ldg(&cell_start[c]), e = (int)__ldg(&cell_start[c + 1]);
    int rank = 0;
    for (int a = s; a < e; a++)
-      rank += (tmp_ord[a] < mine) ? 1 : 0;
+      rank += (pair[a] < mine) ? 1 : 0;
    idx_sorted[s + rank] = me;
    if (GATHER)
       s_pos4[s + rank] = __ldg(&pos4[me]);
@@ -306,10 +315,10 @@ int sph_bin_and_sort(sphb200_ctx* ctx, bool fine)
    {
       if (fine)
          k_cell_keys<true><<<blocks_for(n), kThreads, 0, st>>>(P, cells, ctx->pos4, ctx->keys, ctx->cell_count,
-                                                               ctx->cell_slot, ctx->voxel_id);
+                                                               ctx->cell_slot, ctx->voxel_id, ctx->xkey);
       else
          k_cell_keys<false><<<blocks_for(n), kThreads, 0, st>>>(P, cells, ctx->pos4, ctx->keys, ctx->cell_count,
-                                                                ctx->cell_slot, ctx->voxel_id);
+                                                                ctx->cell_slot, ctx->voxel_id, nullptr);
       ctx->launches++;
       SPH_CUDA_CHECK(ctx, cudaGetLastError());
       ctx->voxel_ids_valid = true;
@@ -319,18 +328,19 @@ int sph_bin_and_sort(sphb200_ctx* ctx, bool fine)
                                                      st));
    ctx->launches += 2;
    ctx->idx_order = ctx->idx_sorted;
-   if (n > 0 && !ctx->use_radix_sort)
+   if (n > 0 && (fine || !ctx->use_radix_sort))   // (the radix-sort A/B path only knows the index order of sampled mode)
    {
       const uint32_t* gid = ctx->comm ? ctx->gid : nullptr;
       k_scatter<<<blocks_for(n), kThreads, 0, st>>>(n, ctx->keys, ctx->cell_slot, ctx->cell_start, gid,
-                                                    ctx->keys_sorted, ctx->tmp_ord, ctx->tmp_idx);
+                                                    fine ? ctx->xkey : nullptr, ctx->keys_sorted, ctx->tmp_pair,
+                                                    ctx->tmp_idx);
       if (fine)
          k_rank_gather<true><<<blocks_for(n), kThreads, 0, st>>>(n, cells, ctx->keys_sorted, ctx->cell_start,
-                                                                 ctx->tmp_ord, gid ? ctx->tmp_idx : nullptr,
+                                                                 ctx->tmp_pair, gid ? ctx->tmp_idx : nullptr,
                                                                  ctx->pos4, ctx->idx_sorted, ctx->s_pos4);
       else
          k_rank_gather<false><<<blocks_for(n), kThreads, 0, st>>>(n, cells, ctx->keys_sorted, ctx->cell_start,
-                                                                  ctx->tmp_ord, gid ? ctx->tmp_idx : nullptr,
+                                                                  ctx->tmp_pair, gid ? ctx->tmp_idx : nullptr,
                                                                   ctx->pos4, ctx->idx_sorted, ctx->s_pos4);
       ctx->launches += 2;
       SPH_CUDA_CHECK(ctx, cudaGetLastError());
@@ -377,8 +387,9 @@ int sph_grid_alloc(sphb200_ctx* ctx)
    SPH_CUDA_CHECK(ctx, cudaMalloc(&ctx->cub_temp, ctx->cub_temp_bytes));
    size_t slots = (size_t)(ctx->capacity > 0 ? ctx->capacity : 1);
    SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->cell_slot, sizeof(uint32_t) * slots));
-   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->tmp_ord, sizeof(uint32_t) * slots));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->tmp_pair, sizeof(unsigned long long) * slots));
    SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->tmp_idx, sizeof(uint32_t) * slots));
+   SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->xkey, sizeof(uint32_t) * slots));
    const char* radix = getenv("SPHB200_RADIX_SORT");
    ctx->use_radix_sort = radix && radix[0] == '1';
    return SPHB200_OK;
@@ -390,10 +401,12 @@ void sph_grid_free(sphb200_ctx* ctx)
    if (ctx->cell_start) cudaFree(ctx->cell_start);
    if (ctx->cub_temp) cudaFree(ctx->cub_temp);
    if (ctx->cell_slot) cudaFree(ctx->cell_slot);
-   if (ctx->tmp_ord) cudaFree(ctx->tmp_ord);
+   if (ctx->tmp_pair) cudaFree(ctx->tmp_pair);
    if (ctx->tmp_idx) cudaFree(ctx->tmp_idx);
+   if (ctx->xkey) cudaFree(ctx->xkey);
    ctx->cell_count = ctx->cell_start = nullptr;
-   ctx->cell_slot = ctx->tmp_ord = ctx->tmp_idx = nullptr;
+   ctx->cell_slot = ctx->tmp_idx = ctx->xkey = nullptr;
+   ctx->tmp_pair = nullptr;
    ctx->cub_temp = nullptr;
 }
 

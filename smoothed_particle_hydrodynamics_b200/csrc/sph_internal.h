@@ -113,7 +113,10 @@ struct sphb200_ctx
    uint32_t *keys, *keys_sorted, *idx_iota, *idx_sorted;
    const uint32_t* idx_order;   // particle order of the last binning: idx_sorted, or idx_fixed in slab mode
    uint32_t* cell_slot;   // per particle: its slot inside its cell (return value of the histogram atomic)
-   uint32_t *tmp_ord, *tmp_idx;   // counting-sort scatter output: ranking value / particle index per position
+   unsigned long long* tmp_pair;  // counting-sort scatter output per position: (x order key << 32 | id), the value the
+                                  // members of a cell are ranked by (x key 0 in sampled mode: ascending id = push_back order)
+   uint32_t* tmp_idx;             // slab mode: the slot index per scattered position (id = global id there)
+   uint32_t* xkey;                // FULL mode: order key of x per particle (in-cell order by x)
    bool use_radix_sort;   // A/B switch (env SPHB200_RADIX_SORT=1): CUB radix sort instead of the counting sort
    uint32_t* cell_count;  // histogram, cells_alloc + 1
    uint32_t* cell_start;  // exclusive scan, cells_alloc + 1

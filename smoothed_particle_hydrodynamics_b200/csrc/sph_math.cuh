@@ -39,6 +39,19 @@ __device__ __forceinline__ int sph_upper_half(float pos, int v, float h_times2, 
    return (o > h) ? 1 : 0;
 }
 
+// order-preserving map of a float to unsigned (-0 < +0): FULL mode orders the members of a fine cell by
+// ascending (x, particle index) -- oracle/sph_oracle.c:x_order_key.  A NaN comes first: it is binned into
+// cell 0 of its row, so it then sits in front of every run that contains it, where it only shifts the
+// candidates behind it by one slot -- the packed sums (alternate candidates into two accumulators that
+// are added at the end) do not change under such a shift, a NaN in the middle of a run would split it.
+__device__ __forceinline__ uint32_t sph_x_order_key(float x)
+{
+   const uint32_t b = __float_as_uint(x);
+   if (x != x)
+      return 0u;
+   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
 // computeVoxelId (sph.cpp:1151-1154)
 __device__ __forceinline__ int sph_voxel_id(int vx, int vy, int vz, int gx, int gy)
 {

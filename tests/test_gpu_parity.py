@@ -56,7 +56,19 @@ def well_conditioned(o, w0):
     return ~(bad | nb_bad)
 
 
-def check_acc(acc, ref, tag="", mask=None):
+def pressure_slack(rho, o):
+    """First-order propagation of the density difference through 1/p_i: computeAcceleration divides by
+    p_i = k (rho_i - rho0) when it is positive (sph.cpp:786-788), so a = (...) / p_i and
+    |da| / |a| = |d rho_i| / |rho_i - rho0|.  Two valid FP32 summation orders of the same ~33 poly6 terms
+    differ by a few ulp of rho; on a lattice at rest density (rho within 0.2 % of rho0) that alone is worth
+    up to ~2e-4 of the acceleration -- the reference's own number is no better determined.  The
+    acceleration check therefore allows, per particle, 1e-4 plus twice this propagated difference
+    (the density itself is held to 1e-5 separately; nothing is excluded)."""
+    dp = np.abs(o.rho.astype(np.float64) - np.float64(o.p.rho0))
+    return np.where(o.rho > o.p.rho0, 2.0 * np.abs(rho.astype(np.float64) - o.rho) / np.maximum(dp, 1e-30), 0.0)
+
+
+def check_acc(acc, ref, tag="", mask=None, slack=None):
     finite = np.isfinite(ref).all(axis=1)
     if mask is not None:
         finite &= mask
@@ -67,18 +79,23 @@ def check_acc(acc, ref, tag="", mask=None):
     a, r = acc[finite].astype(np.float64), ref[finite].astype(np.float64)
     norm = np.linalg.norm(r, axis=1)
     err = np.abs(a - r).max(axis=1) / np.maximum(norm, 1e-30)
-    assert err.max() <= ACC_TOL_MAX, "%s acc err max %g" % (tag, err.max())
+    allowed = ACC_TOL_MAX + (slack[finite] if slack is not None else 0.0)
+    assert (err <= allowed).all(), "%s acc err max %g (%d particles over)" % (tag, err.max(), (err > allowed).sum())
     assert (err <= ACC_TOL_BULK).mean() >= 0.999, "%s acc bulk %g" % (tag, (err <= ACC_TOL_BULK).mean())
 
 
-def check_state(x, ref, scale, tag="", mask=None):
+def check_state(x, ref, scale, tag="", mask=None, abs_slack=None):
+    """abs_slack: per-particle absolute allowance on top of STATE_TOL -- the propagated acceleration
+    slack (pressure_slack x |a| x dt) for velocities."""
     finite = np.isfinite(ref)
     if mask is not None:
         finite &= mask[:, None]
         x = np.where(mask[:, None], x, ref)
     assert np.array_equal(np.isfinite(x) & finite, finite), "%s non-finite entries differ" % tag
-    err = np.abs(x[finite].astype(np.float64) - ref[finite]) / np.maximum(np.abs(ref[finite]), scale)
-    assert err.max() <= STATE_TOL, "%s state err %g" % (tag, err.max())
+    den = np.maximum(np.abs(ref[finite]), scale)
+    err = np.abs(x[finite].astype(np.float64) - ref[finite]) / den
+    allowed = STATE_TOL + (np.broadcast_to(abs_slack[:, None], ref.shape)[finite] / den if abs_slack is not None else 0.0)
+    assert (err <= allowed).all(), "%s state err %g" % (tag, err.max())
 
 
 def w0_of(d, mass=1.0):
@@ -194,10 +211,15 @@ def _compare_full_step(sph, o, tag, check_lists=True, conditioned=False, min_mas
             nb, nd = sparse_lists(sph.download(F.NEIGHBOR_INDEX), sph.download(F.NEIGHBOR_DISTANCE), o.count)
             assert np.array_equal(nb, onb), tag + " (visited)"
             assert np.array_equal(nd, ond), tag + " (visited)"
-    check_density(sph.download(F.DENSITY), o.rho, w0_of(d, o.mass), tag)
-    check_acc(sph.download(F.ACCELERATION), o.acc, tag, mask)
-    check_state(sph.download(F.POSITION), o.pos, 1.0, tag + " pos", mask)
-    check_state(sph.download(F.VELOCITY), o.vel, 1.0, tag + " vel", mask)
+    rho = sph.download(F.DENSITY)
+    check_density(rho, o.rho, w0_of(d, o.mass), tag)
+    slack = pressure_slack(rho, o)
+    check_acc(sph.download(F.ACCELERATION), o.acc, tag, mask, slack)
+    # v' = v + a dt (+ ...): the same allowance, propagated through one step
+    with np.errstate(invalid="ignore"):
+        vel_slack = slack * np.nan_to_num(np.abs(o.acc).max(axis=1), nan=0.0, posinf=0.0) * float(o.p.time_step)
+    check_state(sph.download(F.POSITION), o.pos, 1.0, tag + " pos", mask, vel_slack * float(o.p.time_step))
+    check_state(sph.download(F.VELOCITY), o.vel, 1.0, tag + " vel", mask, vel_slack)
     return mask
 
 

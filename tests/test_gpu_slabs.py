@@ -88,8 +88,15 @@ def test_virtual_slabs_reproduce_single_gpu_run(nranks, mode):
         finite = np.isfinite(acc_ref).all(axis=1)
         assert finite.mean() > 0.99
         assert np.array_equal(_gather(slabs, F.ACCELERATION)[0][finite], acc_ref[finite])
-        assert np.array_equal(_gather(slabs, F.POSITION)[0], ref.download(F.POSITION), equal_nan=True)
-        assert np.array_equal(_gather(slabs, F.VELOCITY)[0], ref.download(F.VELOCITY), equal_nan=True)
+        # (a state with a NaN in ANY component is degenerate as a whole: the single run keeps integrating it
+        # -- NaN acceleration, every component NaN a step later -- while a slab parks it until it reaches
+        # rank 0; such rows only have to be degenerate on both sides)
+        for fld in (F.POSITION, F.VELOCITY):
+            got, want = _gather(slabs, fld)[0], ref.download(fld)
+            degenerate = ~np.isfinite(ref.download(F.POSITION)).all(axis=1) | ~np.isfinite(want).all(axis=1)
+            assert np.array_equal(got[~degenerate], want[~degenerate])
+            assert (~np.isfinite(got[degenerate])).any(axis=1).all()
+            assert degenerate.mean() < 0.01
         assert np.array_equal(_gather(slabs, F.MASS)[0], mass)
     owned1 = [s.local_count() for s in slabs]
     assert sum(o for o, _ in owned1) == n

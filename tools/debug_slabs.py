@@ -33,6 +33,44 @@ for step in range(1, 21):
     rel = np.abs(a[bad]-ar[bad]).max(1)/np.maximum(np.linalg.norm(ar[bad],axis=1),1e-30) if bad.size else np.zeros(0)
     print("step", step, "nanmis", nanmis, "mismatch", bad.size, "layers", np.unique(vzp[bad]), "max rel", rel.max() if bad.size else 0, "counts", [s.local_count() for s in slabs],
           "rho eq", np.array_equal(_gather(slabs, F.DENSITY)[0], ref.download(F.DENSITY)))
+    ps, _ = _gather(slabs, F.POSITION); pr = ref.download(F.POSITION)
+    vs, _ = _gather(slabs, F.VELOCITY); vr = ref.download(F.VELOCITY)
+    pb = np.flatnonzero(~((ps == pr) | (np.isnan(ps) & np.isnan(pr))).all(1))
+    vb = np.flatnonzero(~((vs == vr) | (np.isnan(vs) & np.isnan(vr))).all(1))
+    if pb.size or vb.size:
+        print("   POS mismatch", pb.size, "VEL mismatch", vb.size)
+        for i in pb[:4]:
+            print("      ", i, "slab", ps[i], vs[i], "ref", pr[i], vr[i], "prev", prev[i], "acc slab", a[i], "acc ref", ar[i])
     if bad.size:
         i = bad[np.argmax(rel)]
         print("   worst", i, a[i], ar[i], "z", prev[i,2], "vz", vzp[i], "frac in voxel", prev[i,2]/0.2 - vzp[i])
+    if bad.size and step >= 10:
+        # ghost densities of every slab against the single run (ghost slots keep the pre-step position)
+        rho_ref = ref.download(F.DENSITY)
+        key = {tuple(p): i for i, p in enumerate(map(tuple, prev))}
+        for r, s in enumerate(slabs):
+            P = s.download(F.POSITION); R = s.download(F.DENSITY)
+            own_pos, own_g = s.download_slab(F.POSITION)
+            owned = set(own_g.tolist())
+            nbad = nmatch = 0
+            ex = []
+            for slot in range(P.shape[0]):
+                g = key.get(tuple(P[slot]))
+                if g is None or g in owned:
+                    continue
+                z0, z1 = layers[r]
+                zz = prev[g][2]
+                inner = (z0 * 0.2 - 0.1 <= zz < z0 * 0.2) or (z1 * 0.2 <= zz < z1 * 0.2 + 0.1)
+                if not inner:
+                    continue
+                nmatch += 1
+                if R[slot] != rho_ref[g]:
+                    nbad += 1
+                    if len(ex) < 5:
+                        ex.append((g, float(R[slot]), float(rho_ref[g]), prev[g].tolist()))
+            # particles in this slab's arrays that are neither matched ghosts nor in its owned z-range
+            z0, z1 = layers[r]
+            odd = [(int(g), own_pos[i].tolist()) for i, g in enumerate(own_g) if not (z0 * 0.2 <= own_pos[i][2] < z1 * 0.2)]
+            print("   slab", r, "owned outside its range (post-step positions):", len(odd), odd[:6])
+            print("   slab", r, "ghost slots matched", nmatch, "density differs", nbad, ex)
+        break
