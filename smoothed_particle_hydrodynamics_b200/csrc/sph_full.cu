@@ -78,6 +78,13 @@ constexpr int kTileThreads = SPH_TILE_THREADS;
 constexpr int kTileCtas = SPH_TILE_CTAS;    // resident CTAs per SM the kernel is built for
 constexpr int kCap = SPH_CAP;               // staged particles per (sub-)tile, equal masses (12 B each)
 constexpr int kCapMass = (12 * (kCap + 4)) / 16 - 4;   // ... with per-particle masses (16 B each): same bytes
+#ifndef SPH_DENS_XTRIM
+#define SPH_DENS_XTRIM 1         // 1: the density sweep cuts every x-run down to |dx| < h before testing candidates (the runs
+                                 // are ascending in x since the in-cell order is by x): per halo row a table of the first
+                                 // staged slot at or above each quarter-cell threshold, two lookups per run
+#endif
+constexpr int XQ = 4;                           // x thresholds per cell edge
+constexpr int XT = (TBX + 2) * XQ + 2;          // table entries per halo row: thresholds 0 .. (TBX+2)*XQ, + the end
 constexpr int kPairCap = (kCap + TBX * TBY * TBZ) / 2 + 1;   // pairs of a staged tile: sum over cells of ceil(count / 2)
 static_assert(kCap < 32768, "a pair's first target number has 15 bits");
 static_assert(TBX * TBY * TBZ <= kTileThreads, "one thread per target cell builds the pair table");
@@ -155,6 +162,9 @@ struct TileLayout
    int total;                // staged particles
    int ntargets;
    int rowk[TROWS];          // sorted index of target t of row r = rowk[r] + t
+#if SPH_DENS_XTRIM
+   unsigned short xtab[HROWS][XT];   // per halo row: first staged slot whose x threshold index is >= t
+#endif
 #if SPH_DENS_PAIR
    int npairs;               // work items of the packed sweep: one or two targets of one cell
    int wsum[32];
@@ -809,27 +819,64 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
 // group -- {x0 x1 x2 x3}{y0..y3}{z0..z3}[{m0..m3}] -- so that one LDS.128 per
 // coordinate feeds two packed instructions (candidates 0,1 and 2,3).  Staged index s
 // lives in group s >> 2, lane s & 3.  Equal masses (UMASS) drop the fourth row.
+// x threshold index of a coordinate: floor(x * XQ / h) relative to the tile's first halo cell, clamped to the
+// table.  ONE function for candidates (table build) and targets (lookups): it is monotone in x, so "every
+// candidate with x >= lo has an index >= index(lo)" holds whatever the rounding.  NaN -> 0 (they come first).
+__device__ __forceinline__ int x_threshold(float x, float inv_q, int m0, int hi)
+{
+   return min(max(__float2int_rd(x * inv_q) - m0, 0), hi);     // cvt.rmi saturates; NaN converts to 0
+}
+
 template <bool UMASS>
-__device__ __forceinline__ void stage_rows_packed(const SubTile& t, const TileLayout& L,
+__device__ __forceinline__ void stage_rows_packed(const DevParams& P, const SubTile& t, TileLayout& L,
                                                   const float4* __restrict__ src, float* __restrict__ sg)
 {
    constexpr int GF = UMASS ? 12 : 16;   // floats per group
    const int rows = (t.by + 2) * (t.bz + 2);
    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#if SPH_DENS_XTRIM
+   const float inv_q = P.h_times2_inv * (2.0f * XQ);     // XQ / h
+   const int m0 = (t.x0 - 1) * XQ, mt = (t.bx + 2) * XQ; // thresholds 0 .. mt cover the halo row's cells
+#endif
    for (int hr = warp; hr < rows; hr += nwarps)
    {
       int g0 = L.row_g0[hr], len = L.row_len[hr], off = g0 + L.row_delta[hr];
-      for (int j = lane; j < len; j += 32)
+#if SPH_DENS_XTRIM
+      int m_carry = -1;      // threshold index of the previous particle of the row
+#endif
+      for (int j0 = 0; j0 < len; j0 += 32)
       {
-         float4 p = __ldg(&src[g0 + j]);
-         int s = off + j;
-         float* d = sg + (s >> 2) * GF + (s & 3);
-         d[0] = p.x;
-         d[4] = p.y;
-         d[8] = p.z;
-         if (!UMASS)
-            d[12] = p.w;
+         const int j = j0 + lane;
+         float4 p = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+         if (j < len)
+         {
+            p = __ldg(&src[g0 + j]);
+            int s = off + j;
+            float* d = sg + (s >> 2) * GF + (s & 3);
+            d[0] = p.x;
+            d[4] = p.y;
+            d[8] = p.z;
+            if (!UMASS)
+               d[12] = p.w;
+         }
+#if SPH_DENS_XTRIM
+         // xtab[t] = first staged slot of the row whose index is >= t: a particle fills the thresholds
+         // between its left neighbour's index (exclusive) and its own (inclusive); the row is ascending in x
+         int m = j < len ? x_threshold(p.x, inv_q, m0, mt) : mt;
+         int left = __shfl_up_sync(0xffffffffu, m, 1);
+         if (lane == 0)
+            left = m_carry;
+         if (j < len)
+            for (int q = left + 1; q <= m; q++)
+               L.xtab[hr][q] = (unsigned short)(off + j);
+         m_carry = __shfl_sync(0xffffffffu, m, min(31, len - 1 - j0));   // the last particle of this block of 32
+#endif
       }
+#if SPH_DENS_XTRIM
+      // thresholds above the last particle (all of them in an empty row) point at the row's end
+      for (int q = m_carry + 1 + lane; q <= mt + 1; q += 32)
+         L.xtab[hr][q] = (unsigned short)(off + len);
+#endif
       // runs are widened to whole groups: the unused lanes of the row's last group hold
       // a position that is far from everything (and no mass)
       int s = off + len + lane;
@@ -917,6 +964,10 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
    const f32x2 NH = pack2(-P.hs2, -P.hs2), NTHR = pack2(-thr, -thr), S2 = pack2(scale2, scale2);
    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sg);
    const int rowstep = t.by + 2;
+#if SPH_DENS_XTRIM
+   const float inv_q = P.h_times2_inv * (2.0f * XQ);     // XQ / h
+   const int m0 = (t.x0 - 1) * XQ, mt = (t.bx + 2) * XQ;
+#endif
    for (int tnum = threadIdx.x; tnum < L.ntargets; tnum += blockDim.x)
    {
       Target T = locate_target(L, tnum);
@@ -934,16 +985,34 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
       // the 9 runs in ascending row order: (z-1: y-1, y, y+1), (z: ...), (z+1: ...)
       const int* csp = &L.cs[T.hr0 - rowstep - 1][T.lx - 1];
       const int* dlp = &L.row_delta[T.hr0 - rowstep - 1];
+#if SPH_DENS_XTRIM
+      // a run is ascending in x: only its candidates with |dx| < h (1.001 h: the margin covers the rounding
+      // of x -+ w by orders of magnitude) can be neighbours.  Two table lookups per run give the first staged
+      // slot at / above the quarter-cell threshold below x - w and the first one above x + w.
+      const float w = 1.001f * P.h;
+      // (index 0 also holds everything left of the table, index mt everything right of it: the upper bound is
+      // at least threshold 1, the lower one at most mt)
+      const int mlo = x_threshold(pi.x - w, inv_q, m0, mt), mhi = max(x_threshold(pi.x + w, inv_q, m0 - 1, mt + 1), 1);
+      const unsigned short* xtp = &L.xtab[T.hr0 - rowstep - 1][0];
+#endif
 #pragma unroll kDensUnroll
       for (int r = 0; r < 9; r++)
       {
          f32x2 sum2 = pack2(0.0f, 0.0f);
          const int delta = dlp[0];
+#if SPH_DENS_XTRIM
+         const int b = max(csp[0] + delta, (int)xtp[mlo]);
+         const int e = min(csp[3] + delta, (int)xtp[mhi]);
+#else
          const int b = csp[0] + delta;
          const int e = csp[3] + delta;
+#endif
          const bool last_of_plane = (r == 2 || r == 5);
          csp += last_of_plane ? (rowstep - 2) * CSW : CSW;
          dlp += last_of_plane ? rowstep - 2 : 1;
+#if SPH_DENS_XTRIM
+         xtp += last_of_plane ? (rowstep - 2) * XT : XT;
+#endif
 #pragma unroll 1
          for (int c0 = b & ~3; c0 < e; c0 += 32)
          {
@@ -1223,7 +1292,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtas)
             {
                if (level < 4)
                {
-                  stage_rows_packed<UMASS>(t, L, s_pos4, sg);
+                  stage_rows_packed<UMASS>(P, t, L, s_pos4, sg);
                   __syncthreads();
 #if SPH_DENS_PAIR
                   density_pairs_packed<UNIT, UMASS>(P, t, L, sg, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho,
