@@ -83,7 +83,10 @@ constexpr int kCapMass = (12 * (kCap + 4)) / 16 - 4;   // ... with per-particle 
                                  // are ascending in x since the in-cell order is by x): per halo row a table of the first
                                  // staged slot at or above each quarter-cell threshold, two lookups per run
 #endif
-constexpr int XQ = 4;                           // x thresholds per cell edge
+#ifndef SPH_XQ
+#define SPH_XQ 4
+#endif
+constexpr int XQ = SPH_XQ;                      // x thresholds per cell edge
 constexpr int XT = (TBX + 2) * XQ + 2;          // table entries per halo row: thresholds 0 .. (TBX+2)*XQ, + the end
 constexpr int kPairCap = (kCap + TBX * TBY * TBZ) / 2 + 1;   // pairs of a staged tile: sum over cells of ceil(count / 2)
 static_assert(kCap < 32768, "a pair's first target number has 15 bits");
@@ -1145,6 +1148,10 @@ __device__ __forceinline__ void density_pairs_packed(const DevParams& P, const S
    const f32x2 NH = pack2(-P.hs2, -P.hs2), NTHR = pack2(-thr, -thr), S2 = pack2(scale2, scale2);
    const unsigned sbase = (unsigned)__cvta_generic_to_shared(sg);
    const int rowstep = t.by + 2;
+#if SPH_DENS_XTRIM
+   const float inv_q = P.h_times2_inv * (2.0f * XQ);     // XQ / h
+   const int m0 = (t.x0 - 1) * XQ, mt = (t.bx + 2) * XQ;
+#endif
    for (int pn = threadIdx.x; pn < L.npairs; pn += blockDim.x)
    {
       const unsigned code = L.pcode[pn], tg = L.ptgt[pn];
@@ -1162,15 +1169,30 @@ __device__ __forceinline__ void density_pairs_packed(const DevParams& P, const S
       // the 9 runs in ascending row order: (z-1: y-1, y, y+1), (z: ...), (z+1: ...)
       const int* csp = &L.cs[hr0 - rowstep - 1][lx - 1];
       const int* dlp = &L.row_delta[hr0 - rowstep - 1];
+#if SPH_DENS_XTRIM
+      // the window of the pair: from the lower target's x - w to the upper target's x + w (see density_targets_packed)
+      const float w = 1.001f * P.h;
+      const int mlo = x_threshold(fminf(pa.x, pb.x) - w, inv_q, m0, mt);
+      const int mhi = max(x_threshold(fmaxf(pa.x, pb.x) + w, inv_q, m0 - 1, mt + 1), 1);
+      const unsigned short* xtp = &L.xtab[hr0 - rowstep - 1][0];
+#endif
 #pragma unroll kDensUnroll
       for (int r = 0; r < 9; r++)
       {
          const int delta = dlp[0];
+#if SPH_DENS_XTRIM
+         const int b = max(csp[0] + delta, (int)xtp[mlo]);
+         const int e = min(csp[3] + delta, (int)xtp[mhi]);
+#else
          const int b = csp[0] + delta;
          const int e = csp[3] + delta;
+#endif
          const bool last_of_plane = (r == 2 || r == 5);
          csp += last_of_plane ? (rowstep - 2) * CSW : CSW;
          dlp += last_of_plane ? rowstep - 2 : 1;
+#if SPH_DENS_XTRIM
+         xtp += last_of_plane ? (rowstep - 2) * XT : XT;
+#endif
 #pragma unroll 1
          for (int c0 = b & ~3; c0 < e; c0 += 32)
          {
