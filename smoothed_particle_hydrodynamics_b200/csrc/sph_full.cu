@@ -27,6 +27,8 @@
 // that, processed straight from global memory (scalar arithmetic, scan based).
 // In slab mode (multi-GPU) the force sweep also appends its boundary-layer particles
 // and migrants to the next halo messages (sph_slab_emit, sph_math.cuh).
+#include <type_traits>
+
 #include "sph_math.cuh"
 
 namespace
@@ -93,6 +95,8 @@ static_assert(kCap < 32768, "a pair's first target number has 15 bits");
 static_assert(TBX * TBY * TBZ <= kTileThreads, "one thread per target cell builds the pair table");
 constexpr int WCAP = 32;                    // hit-mask records per particle (32 candidates each)
 constexpr unsigned kNoStream = 0xffu;       // info.nw value: no stream, scan instead
+constexpr unsigned kRunShift = 28;          // record base: sorted index | x-run number << 28
+constexpr unsigned kBaseMask = (1u << kRunShift) - 1u;
 #ifndef SPH_FORCE_RSM
 #define SPH_FORCE_RSM 10   // 16: 2.49 ms, 12: 2.42, 10 and 8: 2.41, 6: 2.47, 4: 2.56 -- shared memory given up here is L1 for the gathers
 #endif
@@ -1351,10 +1355,9 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
                   float4* __restrict__ s_acc4, int* __restrict__ s_count, double* __restrict__ block_partials,
                   StepScalars* scal, cudaTextureObject_t tex_posA, cudaTextureObject_t tex_velB)
 {
-   __shared__ unsigned rmask_all[RSM * kForceThreads];
-   __shared__ unsigned rbase_all[RSM * kForceThreads];
-   unsigned* rmask = rmask_all + threadIdx.x;
-   unsigned* rbase = rbase_all + threadIdx.x;
+   // the first RSM records of every thread, {mask, sorted index of the chunk's first candidate}, as one
+   // 8-byte word each: record w of thread t at rrec_all[w * kForceThreads + t]
+   __shared__ uint2 rrec_all[RSM * kForceThreads];
    const int k = blockIdx.x * kForceThreads + threadIdx.x;
    bool active = k < sph_live_count(P);
    if (P.slab && active)
@@ -1381,8 +1384,8 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    for (int w = 0; w < min(nw, RSM); w++)
    {
       uint2 r2 = SPH_LD_ONCE(rec + (size_t)w * 32);
-      rmask[w * kForceThreads] = r2.x;
-      rbase[w * kForceThreads] = r2.y;
+      r2.y &= kBaseMask;
+      rrec_all[w * kForceThreads + threadIdx.x] = r2;
    }
    ForceI I = make_force_i(P, pi, vi, rho_i);
    Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
@@ -1390,21 +1393,22 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    int w = 0;
    unsigned m = 0;
    int base = 0;
+   const uint2* rnext = rrec_all + threadIdx.x;     // this thread's next record in shared memory
    // sorted index of this lane's next hit (records with an empty mask are never stored)
    auto next_hit = [&]() -> int {
       if (m == 0u)
       {
+         uint2 r2;
          if (w < RSM)
-         {
-            m = rmask[w * kForceThreads];
-            base = (int)(rbase[w * kForceThreads] & 0x0fffffffu);
-         }
+            r2 = *rnext;
          else
          {
-            uint2 r2 = SPH_LD_ONCE(rec + (size_t)w * 32);
-            m = r2.x;
-            base = (int)(r2.y & 0x0fffffffu);
+            r2 = SPH_LD_ONCE(rec + (size_t)w * 32);
+            r2.y &= kBaseMask;
          }
+         m = r2.x;
+         base = (int)r2.y;
+         rnext += kForceThreads;
          w++;
       }
       int lead = __clz((int)m);
@@ -1412,18 +1416,22 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
       return base + lead;
    };
    // kForceIlp hits per trip: their gathers and arithmetic are independent (ILP); only the
-   // accumulation is ordered (the in-loop viscosity scaling, sph.cpp:880-882)
-   const int nmax = __reduce_max_sync(0xffffffffu, nhits);
-#pragma unroll 1
-   for (int it = 0; it < nmax; it += kForceIlp)
-   {
+   // accumulation is ordered (the in-loop viscosity scaling, sph.cpp:880-882).  CHECKED = false:
+   // every lane of the warp still has kForceIlp hits left (no per-hit bounds test).
+   auto trip = [&](int it, auto checked) {
+      constexpr bool CHECKED = decltype(checked)::value;
       int j[kForceIlp];
       float4 pj[kForceIlp], vj[kForceIlp];
 #pragma unroll
       for (int q = 0; q < kForceIlp; q++)
       {
-         j[q] = kk;
-         if (it + q < nhits)
+         if (CHECKED)
+         {
+            j[q] = kk;
+            if (it + q < nhits)
+               j[q] = next_hit();
+         }
+         else
             j[q] = next_hit();
       }
 #pragma unroll
@@ -1447,7 +1455,16 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
 #pragma unroll
       for (int q = 0; q < kForceIlp; q++)
          force_accumulate(I, t[q], pg, vt, count);
-   }
+   };
+   const int nmax = __reduce_max_sync(0xffffffffu, nhits);
+   const int nmin = (__reduce_min_sync(0xffffffffu, nhits) / kForceIlp) * kForceIlp;
+   int it = 0;
+#pragma unroll 1
+   for (; it < nmin; it += kForceIlp)
+      trip(it, std::false_type());
+#pragma unroll 1
+   for (; it < nmax; it += kForceIlp)
+      trip(it, std::true_type());
    if (scan && active)
    {
       int b[9], e[9];
@@ -1541,8 +1558,6 @@ constexpr int FTROWS = FTY * FTZ;
 constexpr int kFCap = SPH_FCAP;                 // staged particles per tile, 32 bytes each
 constexpr int kFThreads = SPH_FTHREADS;
 static_assert(FHROWS <= 32, "one warp computes the layout of a force tile");
-constexpr unsigned kRunShift = 28;              // record base: sorted index | x-run number << 28
-constexpr unsigned kBaseMask = (1u << kRunShift) - 1u;
 
 struct ForceLayout
 {
