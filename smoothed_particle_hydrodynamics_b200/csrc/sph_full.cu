@@ -1394,12 +1394,14 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    unsigned m = 0;
    int base = 0;
    const uint2* rnext = rrec_all + threadIdx.x;     // this thread's next record in shared memory
-   // sorted index of this lane's next hit (records with an empty mask are never stored)
-   auto next_hit = [&]() -> int {
+   // sorted index of this lane's next hit (records with an empty mask are never stored).  ALL_CACHED: every
+   // record of every lane of the warp sits in shared memory -- the refill is then a handful of predicated
+   // instructions instead of a divergent branch that some lane takes on almost every trip
+   auto next_hit = [&](auto all_cached) -> int {
       if (m == 0u)
       {
          uint2 r2;
-         if (w < RSM)
+         if (decltype(all_cached)::value || w < RSM)
             r2 = *rnext;
          else
          {
@@ -1418,7 +1420,7 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    // kForceIlp hits per trip: their gathers and arithmetic are independent (ILP); only the
    // accumulation is ordered (the in-loop viscosity scaling, sph.cpp:880-882).  CHECKED = false:
    // every lane of the warp still has kForceIlp hits left (no per-hit bounds test).
-   auto trip = [&](int it, auto checked) {
+   auto trip = [&](int it, auto checked, auto all_cached) {
       constexpr bool CHECKED = decltype(checked)::value;
       int j[kForceIlp];
       float4 pj[kForceIlp], vj[kForceIlp];
@@ -1429,10 +1431,10 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
          {
             j[q] = kk;
             if (it + q < nhits)
-               j[q] = next_hit();
+               j[q] = next_hit(all_cached);
          }
          else
-            j[q] = next_hit();
+            j[q] = next_hit(all_cached);
       }
 #pragma unroll
       for (int q = 0; q < kForceIlp; q++)
@@ -1459,12 +1461,21 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    const int nmax = __reduce_max_sync(0xffffffffu, nhits);
    const int nmin = (__reduce_min_sync(0xffffffffu, nhits) / kForceIlp) * kForceIlp;
    int it = 0;
+   if (__all_sync(0xffffffffu, nw <= RSM))
+   {
 #pragma unroll 1
-   for (; it < nmin; it += kForceIlp)
-      trip(it, std::false_type());
+      for (; it < nmin; it += kForceIlp)
+         trip(it, std::false_type(), std::true_type());
 #pragma unroll 1
-   for (; it < nmax; it += kForceIlp)
-      trip(it, std::true_type());
+      for (; it < nmax; it += kForceIlp)
+         trip(it, std::true_type(), std::true_type());
+   }
+   else
+   {
+#pragma unroll 1
+      for (; it < nmax; it += kForceIlp)
+         trip(it, std::true_type(), std::false_type());
+   }
    if (scan && active)
    {
       int b[9], e[9];
