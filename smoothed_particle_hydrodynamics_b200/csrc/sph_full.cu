@@ -168,6 +168,7 @@ struct TileLayout
    int tgt_off[TROWS + 1];   // prefix of target counts per target row
    int total;                // staged particles
    int ntargets;
+   int next_target;          // packed sweep: the next block of 32 targets a warp may take
    int rowk[TROWS];          // sorted index of target t of row r = rowk[r] + t
 #if SPH_DENS_XTRIM
    unsigned short xtab[HROWS][XT];   // per halo row: first staged slot whose x threshold index is >= t
@@ -633,6 +634,7 @@ __device__ void setup_layout(const DevParams& P, const SubTile& t, const uint32_
       {
          L.tgt_off[trows] = incl;
          L.ntargets = incl;
+         L.next_target = 0;
       }
    }
    __syncthreads();
@@ -1019,7 +1021,7 @@ __device__ __forceinline__ void density_group(unsigned a, f32x2 NX, f32x2 NY, f3
 
 #if !SPH_DENS_PAIR
 template <bool UNIT, bool UMASS>
-__device__ __forceinline__ void density_targets_packed(const DevParams& P, const SubTile& t, const TileLayout& L,
+__device__ __forceinline__ void density_targets_packed(const DevParams& P, const SubTile& t, TileLayout& L,
                                                        const float* __restrict__ sg,
                                                        const float4* __restrict__ s_pos4,
                                                        const uint32_t* __restrict__ idx_sorted,
@@ -1037,8 +1039,25 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
    const float inv_q = P.h_times2_inv * (2.0f * XQ);     // XQ / h
    const int m0 = (t.x0 - 1) * XQ, mt = (t.bx + 2) * XQ;
 #endif
+#ifndef SPH_DENS_DYNAMIC
+#define SPH_DENS_DYNAMIC 0       // 1: warps take blocks of 32 targets from a shared counter (A/B: 2.09 against 2.07 ms)
+#endif
+#if SPH_DENS_DYNAMIC
+   for (;;)
+   {
+      int tb = 0;
+      if ((threadIdx.x & 31) == 0)
+         tb = atomicAdd(&L.next_target, 32);
+      tb = __shfl_sync(0xffffffffu, tb, 0);
+      if (tb >= L.ntargets)
+         break;
+      const int tnum = tb + (int)(threadIdx.x & 31);
+      if (tnum >= L.ntargets)
+         continue;
+#else
    for (int tnum = threadIdx.x; tnum < L.ntargets; tnum += blockDim.x)
    {
+#endif
       Target T = locate_target(L, tnum);
       const float4 pi = __ldg(&s_pos4[T.k]);
       const f32x2 NX = pack2(-pi.x, -pi.x), NY = pack2(-pi.y, -pi.y), NZ = pack2(-pi.z, -pi.z);
