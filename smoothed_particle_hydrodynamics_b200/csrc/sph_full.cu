@@ -172,6 +172,7 @@ struct TileLayout
    int rowk[TROWS];          // sorted index of target t of row r = rowk[r] + t
 #if SPH_DENS_XTRIM
    unsigned short xtab[HROWS][XT];   // per halo row: first staged slot whose x threshold index is >= t
+   int xrow_ok[HROWS];               // 0: the row is not ascending in x (see stage_rows_packed): do not trim its runs
 #endif
 #if SPH_DENS_PAIR
    int npairs;               // work items of the packed sweep: one or two targets of one cell
@@ -877,8 +878,8 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
       else
          hit_info[T.k] = kNoStream;
       // the particle itself sat in the centre run with t = hs2: remove its own term (the
-      // reference skips realIndex == particleIndex, sph.cpp:737); a NaN position has term 0
-      float t_self = (pi.x == pi.x && pi.y == pi.y && pi.z == pi.z) ? P.hs2 : 0.0f;
+      // reference skips realIndex == particleIndex, sph.cpp:737); a NaN or infinite position has term 0
+      float t_self = (pi.x - pi.x == 0.0f && pi.y - pi.y == 0.0f && pi.z - pi.z == 0.0f) ? P.hs2 : 0.0f;   // (inf - inf is NaN too)
       float self = UMASS ? (t_self * t_self) * t_self : __fmul_rn(pi.w * t_self, t_self * t_self);
       float rho = UMASS ? (P.k1 * pi.w) * (sum - self) : P.k1 * (sum - self);
       density_store(P, T.k, pi, rho, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
@@ -895,7 +896,10 @@ __device__ __forceinline__ void density_targets(const DevParams& P, const SubTil
 // candidate with x >= lo has an index >= index(lo)" holds whatever the rounding.  NaN -> 0 (they come first).
 __device__ __forceinline__ int x_threshold(float x, float inv_q, int m0, int hi)
 {
-   return min(max(__float2int_rd(x * inv_q) - m0, 0), hi);     // cvt.rmi saturates; NaN converts to 0
+   // the offset is subtracted in float (exact for every value near the table: both operands are below 2^24
+   // quarter-cells and the difference is smaller than either) so that the conversion saturates for the
+   // far-out-of-box values instead of an integer subtraction wrapping around; NaN converts to 0
+   return min(max(__float2int_rd(x * inv_q - (float)m0), 0), hi);
 }
 
 template <bool UMASS>
@@ -914,6 +918,8 @@ __device__ __forceinline__ void stage_rows_packed(const DevParams& P, const SubT
       int g0 = L.row_g0[hr], len = L.row_len[hr], off = g0 + L.row_delta[hr];
 #if SPH_DENS_XTRIM
       int m_carry = -1;      // threshold index of the previous particle of the row
+      bool descends = false; // a row is ascending in x unless a position overflowed the reference's (int)floor: such a
+                             // particle (x * 1/(2h) >= 2^31) is binned into cell 0 like a NaN but sorts last there
 #endif
       for (int j0 = 0; j0 < len; j0 += 32)
       {
@@ -938,8 +944,11 @@ __device__ __forceinline__ void stage_rows_packed(const DevParams& P, const SubT
          if (lane == 0)
             left = m_carry;
          if (j < len)
+         {
+            descends |= m < left;
             for (int q = left + 1; q <= m; q++)
                L.xtab[hr][q] = (unsigned short)(off + j);
+         }
          m_carry = __shfl_sync(0xffffffffu, m, min(31, len - 1 - j0));   // the last particle of this block of 32
 #endif
       }
@@ -947,6 +956,9 @@ __device__ __forceinline__ void stage_rows_packed(const DevParams& P, const SubT
       // thresholds above the last particle (all of them in an empty row) point at the row's end
       for (int q = m_carry + 1 + lane; q <= mt + 1; q += 32)
          L.xtab[hr][q] = (unsigned short)(off + len);
+      descends = __any_sync(0xffffffffu, descends);
+      if (lane == 0)
+         L.xrow_ok[hr] = descends ? 0 : 1;
 #endif
       // runs are widened to whole groups: the unused lanes of the row's last group hold
       // a position that is far from everything (and no mass)
@@ -1082,6 +1094,7 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
       // at least threshold 1, the lower one at most mt)
       const int mlo = x_threshold(pi.x - w, inv_q, m0, mt), mhi = max(x_threshold(pi.x + w, inv_q, m0 - 1, mt + 1), 1);
       const unsigned short* xtp = &L.xtab[T.hr0 - rowstep - 1][0];
+      const int* xok = &L.xrow_ok[T.hr0 - rowstep - 1];
 #endif
 #pragma unroll kDensUnroll
       for (int r = 0; r < 9; r++)
@@ -1089,8 +1102,9 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
          f32x2 sum2 = pack2(0.0f, 0.0f);
          const int delta = dlp[0];
 #if SPH_DENS_XTRIM
-         const int b = max(csp[0] + delta, (int)xtp[mlo]);
-         const int e = min(csp[3] + delta, (int)xtp[mhi]);
+         const bool trim = xok[0] != 0;
+         const int b = trim ? max(csp[0] + delta, (int)xtp[mlo]) : csp[0] + delta;
+         const int e = trim ? min(csp[3] + delta, (int)xtp[mhi]) : csp[3] + delta;
 #else
          const int b = csp[0] + delta;
          const int e = csp[3] + delta;
@@ -1100,6 +1114,7 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
          dlp += last_of_plane ? rowstep - 2 : 1;
 #if SPH_DENS_XTRIM
          xtp += last_of_plane ? (rowstep - 2) * XT : XT;
+         xok += last_of_plane ? rowstep - 2 : 1;
 #endif
 #pragma unroll 1
          for (int c0 = b & ~3; c0 < e; c0 += 32)
@@ -1162,8 +1177,8 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
       unpack2(sum2b, sa, sb);
       const float sum = -(total + (SPH_DENS_SPLIT_ACC ? sa + sb : 0.0f));
       // the particle itself sat in the centre run with e = -hs2: remove its own term (the
-      // reference skips realIndex == particleIndex, sph.cpp:737); a NaN position has term 0
-      float t_self = (pi.x == pi.x && pi.y == pi.y && pi.z == pi.z) ? P.hs2 : 0.0f;
+      // reference skips realIndex == particleIndex, sph.cpp:737); a NaN or infinite position has term 0
+      float t_self = (pi.x - pi.x == 0.0f && pi.y - pi.y == 0.0f && pi.z - pi.z == 0.0f) ? P.hs2 : 0.0f;   // (inf - inf is NaN too)
       float self = UMASS ? (t_self * t_self) * t_self : __fmul_rn(pi.w * t_self, t_self * t_self);
       float rho = UMASS ? (P.k1 * pi.w) * (sum - self) : P.k1 * (sum - self);
       density_store(P, T.k, pi, rho, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
@@ -1260,14 +1275,16 @@ __device__ __forceinline__ void density_pairs_packed(const DevParams& P, const S
       const int mlo = x_threshold(fminf(pa.x, pb.x) - w, inv_q, m0, mt);
       const int mhi = max(x_threshold(fmaxf(pa.x, pb.x) + w, inv_q, m0 - 1, mt + 1), 1);
       const unsigned short* xtp = &L.xtab[hr0 - rowstep - 1][0];
+      const int* xok = &L.xrow_ok[hr0 - rowstep - 1];
 #endif
 #pragma unroll kDensUnroll
       for (int r = 0; r < 9; r++)
       {
          const int delta = dlp[0];
 #if SPH_DENS_XTRIM
-         const int b = max(csp[0] + delta, (int)xtp[mlo]);
-         const int e = min(csp[3] + delta, (int)xtp[mhi]);
+         const bool trim = xok[0] != 0;
+         const int b = trim ? max(csp[0] + delta, (int)xtp[mlo]) : csp[0] + delta;
+         const int e = trim ? min(csp[3] + delta, (int)xtp[mhi]) : csp[3] + delta;
 #else
          const int b = csp[0] + delta;
          const int e = csp[3] + delta;
@@ -1277,6 +1294,7 @@ __device__ __forceinline__ void density_pairs_packed(const DevParams& P, const S
          dlp += last_of_plane ? rowstep - 2 : 1;
 #if SPH_DENS_XTRIM
          xtp += last_of_plane ? (rowstep - 2) * XT : XT;
+         xok += last_of_plane ? rowstep - 2 : 1;
 #endif
 #pragma unroll 1
          for (int c0 = b & ~3; c0 < e; c0 += 32)
@@ -1349,8 +1367,8 @@ __device__ __forceinline__ void density_pairs_packed(const DevParams& P, const S
          unpack2(tgt ? sumb : suma, sa, sb);
          const float sum = -(sa + sb);
          // the particle itself sat in the centre run with e = -hs2: remove its own term (the
-         // reference skips realIndex == particleIndex, sph.cpp:737); a NaN position has term 0
-         float t_self = (pi.x == pi.x && pi.y == pi.y && pi.z == pi.z) ? P.hs2 : 0.0f;
+         // reference skips realIndex == particleIndex, sph.cpp:737); a NaN or infinite position has term 0
+         float t_self = (pi.x - pi.x == 0.0f && pi.y - pi.y == 0.0f && pi.z - pi.z == 0.0f) ? P.hs2 : 0.0f;   // (inf - inf is NaN too)
          float self = UMASS ? (t_self * t_self) * t_self : __fmul_rn(pi.w * t_self, t_self * t_self);
          float rho = UMASS ? (P.k1 * pi.w) * (sum - self) : P.k1 * (sum - self);
          density_store(P, k, pi, rho, idx_sorted, vel4, s_posA4, s_velB4, s_rho);

@@ -673,3 +673,53 @@ def test_viewer_snapshots_and_step_report(mode):
     assert (rep.e_kin, rep.e_pot, rep.nbr_total, rep.nbr_max, rep.nbr_min) == (ek, ep, tot, mx, mn)
     assert rep.step_index == 6
     sph.close()
+
+
+@pytest.mark.parametrize("variant", [0, 1], ids=["tiled", "flat"])
+def test_full_positions_that_overflow_the_binning(variant):
+    """Positions whose x * 1/(2h) overflows the reference's (int)floor (sph.cpp:452-463: INT_MIN -> voxel 0, like
+    a NaN) sit in cell 0 of their row but sort LAST there by x: the row is then not ascending in x and the
+    density sweep must not trim its runs (the x-threshold table would cut real neighbours off).  Integer outputs,
+    ordered neighbour lists and densities against the oracle on every particle, huge / infinite / NaN
+    coordinates in every axis included."""
+    cfg = scenes.CONFIGS["dambreak_16k"]
+    nx, ny, nz = cfg["sites"]
+    n = nx * ny * nz
+    pos = scenes.lattice_scene(nx, ny, nz, scenes.lattice_spacing(0.1, 40))
+    rng = np.random.default_rng(17)
+    # lattice sites of the first cells of a few rows get degenerate x (and some y / z)
+    first = np.flatnonzero((pos[:, 0] < 0.1))
+    pick = rng.choice(first, 24, replace=False)
+    pos[pick[0:6], 0] = np.float32(3.0e9)          # overflows: binned into voxel 0 in x, sorts last in its cell
+    pos[pick[6:9], 0] = np.float32(-3.0e9)
+    pos[pick[9:12], 0] = np.inf
+    pos[pick[12:15], 0] = np.nan
+    pos[pick[15:18], 1] = np.float32(5.0e9)
+    pos[pick[18:21], 2] = -np.inf
+    pos[pick[21:24], 0] = np.float32(1.0e5)        # far outside, but no overflow: clamped into the LAST voxel
+    # two overflowing particles next to each other: neighbours of one another
+    pos[pick[1]] = pos[pick[0]]
+    pos[pick[1], 1] += np.float32(0.03)
+    vel = np.zeros((n, 3), np.float32)
+    p = _full_params(cfg, n, 96, variant)
+    sph = S.SPH(p, init_scene=False)
+    o = _full_oracle(cfg, n, 96, p)
+    sph.upload(pos, vel)
+    o.set_state(pos, vel)
+    o.step(O_FULL, True, True)
+    sph.step_n(1)
+    assert np.array_equal(sph.download(F.VOXEL_ID), o.voxel_ids)
+    assert np.array_equal(sph.download(F.FINE_KEY), o.fine_keys)
+    cnt = sph.download(F.NEIGHBOR_COUNT)
+    assert np.array_equal(cnt, o.count), np.flatnonzero(cnt != o.count)[:10]
+    assert o.count[pick[0]] >= 1 and o.count[pick[1]] >= 1          # the overflowing pair sees itself
+    sph.build_neighbor_lists()
+    nb, nd = sparse_lists(sph.download(F.NEIGHBOR_INDEX), sph.download(F.NEIGHBOR_DISTANCE), o.count)
+    onb, ond = sparse_lists(o.nbr, o.dist, o.count)
+    assert np.array_equal(nb, onb) and np.array_equal(nd, ond, equal_nan=True)
+    if variant == 0:
+        sph.build_neighbor_lists(visited=True)
+        nb, _ = sparse_lists(sph.download(F.NEIGHBOR_INDEX), None, o.count)
+        assert np.array_equal(nb, onb)
+    check_density(sph.download(F.DENSITY), o.rho, w0_of(sph.derived, o.mass), "overflowing positions")
+    sph.close()
