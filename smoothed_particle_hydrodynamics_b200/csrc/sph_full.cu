@@ -171,8 +171,10 @@ struct TileLayout
    int next_target;          // packed sweep: the next block of 32 targets a warp may take
    int rowk[TROWS];          // sorted index of target t of row r = rowk[r] + t
 #if SPH_DENS_XTRIM
-   unsigned short xtab[HROWS][XT];   // per halo row: first staged slot whose x threshold index is >= t
-   int xrow_ok[HROWS];               // 0: the row is not ascending in x (see stage_rows_packed): do not trim its runs
+   ushort2 xtab[HROWS][XT];          // per halo row and x threshold t: .x = where a run may start when its lower bound
+                                     // has index t, .y = where it must end when its upper bound has index t.  Both are the
+                                     // first staged slot whose index is >= t -- unless the row is not ascending in x
+                                     // (stage_rows_packed): then .x is the row's start and .y its end (no trimming)
 #endif
 #if SPH_DENS_PAIR
    int npairs;               // work items of the packed sweep: one or two targets of one cell
@@ -947,7 +949,7 @@ __device__ __forceinline__ void stage_rows_packed(const DevParams& P, const SubT
          {
             descends |= m < left;
             for (int q = left + 1; q <= m; q++)
-               L.xtab[hr][q] = (unsigned short)(off + j);
+               L.xtab[hr][q] = make_ushort2((unsigned short)(off + j), (unsigned short)(off + j));
          }
          m_carry = __shfl_sync(0xffffffffu, m, min(31, len - 1 - j0));   // the last particle of this block of 32
 #endif
@@ -955,10 +957,13 @@ __device__ __forceinline__ void stage_rows_packed(const DevParams& P, const SubT
 #if SPH_DENS_XTRIM
       // thresholds above the last particle (all of them in an empty row) point at the row's end
       for (int q = m_carry + 1 + lane; q <= mt + 1; q += 32)
-         L.xtab[hr][q] = (unsigned short)(off + len);
-      descends = __any_sync(0xffffffffu, descends);
-      if (lane == 0)
-         L.xrow_ok[hr] = descends ? 0 : 1;
+         L.xtab[hr][q] = make_ushort2((unsigned short)(off + len), (unsigned short)(off + len));
+      if (__any_sync(0xffffffffu, descends))
+      {
+         __syncwarp();
+         for (int q = lane; q <= mt + 1; q += 32)
+            L.xtab[hr][q] = make_ushort2((unsigned short)off, (unsigned short)(off + len));
+      }
 #endif
       // runs are widened to whole groups: the unused lanes of the row's last group hold
       // a position that is far from everything (and no mass)
@@ -1093,8 +1098,7 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
       // (index 0 also holds everything left of the table, index mt everything right of it: the upper bound is
       // at least threshold 1, the lower one at most mt)
       const int mlo = x_threshold(pi.x - w, inv_q, m0, mt), mhi = max(x_threshold(pi.x + w, inv_q, m0 - 1, mt + 1), 1);
-      const unsigned short* xtp = &L.xtab[T.hr0 - rowstep - 1][0];
-      const int* xok = &L.xrow_ok[T.hr0 - rowstep - 1];
+      const ushort2* xtp = &L.xtab[T.hr0 - rowstep - 1][0];
 #endif
 #pragma unroll kDensUnroll
       for (int r = 0; r < 9; r++)
@@ -1102,9 +1106,8 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
          f32x2 sum2 = pack2(0.0f, 0.0f);
          const int delta = dlp[0];
 #if SPH_DENS_XTRIM
-         const bool trim = xok[0] != 0;
-         const int b = trim ? max(csp[0] + delta, (int)xtp[mlo]) : csp[0] + delta;
-         const int e = trim ? min(csp[3] + delta, (int)xtp[mhi]) : csp[3] + delta;
+         const int b = max(csp[0] + delta, (int)xtp[mlo].x);
+         const int e = min(csp[3] + delta, (int)xtp[mhi].y);
 #else
          const int b = csp[0] + delta;
          const int e = csp[3] + delta;
@@ -1114,7 +1117,6 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
          dlp += last_of_plane ? rowstep - 2 : 1;
 #if SPH_DENS_XTRIM
          xtp += last_of_plane ? (rowstep - 2) * XT : XT;
-         xok += last_of_plane ? rowstep - 2 : 1;
 #endif
 #pragma unroll 1
          for (int c0 = b & ~3; c0 < e; c0 += 32)
@@ -1274,17 +1276,15 @@ __device__ __forceinline__ void density_pairs_packed(const DevParams& P, const S
       const float w = 1.001f * P.h;
       const int mlo = x_threshold(fminf(pa.x, pb.x) - w, inv_q, m0, mt);
       const int mhi = max(x_threshold(fmaxf(pa.x, pb.x) + w, inv_q, m0 - 1, mt + 1), 1);
-      const unsigned short* xtp = &L.xtab[hr0 - rowstep - 1][0];
-      const int* xok = &L.xrow_ok[hr0 - rowstep - 1];
+      const ushort2* xtp = &L.xtab[hr0 - rowstep - 1][0];
 #endif
 #pragma unroll kDensUnroll
       for (int r = 0; r < 9; r++)
       {
          const int delta = dlp[0];
 #if SPH_DENS_XTRIM
-         const bool trim = xok[0] != 0;
-         const int b = trim ? max(csp[0] + delta, (int)xtp[mlo]) : csp[0] + delta;
-         const int e = trim ? min(csp[3] + delta, (int)xtp[mhi]) : csp[3] + delta;
+         const int b = max(csp[0] + delta, (int)xtp[mlo].x);
+         const int e = min(csp[3] + delta, (int)xtp[mhi].y);
 #else
          const int b = csp[0] + delta;
          const int e = csp[3] + delta;
@@ -1294,7 +1294,6 @@ __device__ __forceinline__ void density_pairs_packed(const DevParams& P, const S
          dlp += last_of_plane ? rowstep - 2 : 1;
 #if SPH_DENS_XTRIM
          xtp += last_of_plane ? (rowstep - 2) * XT : XT;
-         xok += last_of_plane ? rowstep - 2 : 1;
 #endif
 #pragma unroll 1
          for (int c0 = b & ~3; c0 < e; c0 += 32)
