@@ -473,7 +473,8 @@ int sphb200_destroy(sphb200_ctx* ctx)
                    ctx->slot_state, ctx->idx_fixed, ctx->s_pos4, ctx->s_posA4, ctx->s_rho,
                    ctx->s_acc4, ctx->s_count, ctx->nbr_idx, ctx->nbr_dist, ctx->nbr_count, ctx->rho, ctx->acc4,
                    ctx->voxel_id, ctx->vg_count, ctx->vg_start, ctx->vg_members, ctx->vg_keys,
-                   ctx->d_scalars, ctx->d_block_partials, ctx->stage_f, ctx->hit_rec, ctx->hit_info};
+                   ctx->d_scalars, ctx->d_block_partials, ctx->stage_f, ctx->hit_rec, ctx->hit_info, ctx->tile_list,
+                   ctx->tile_ctl};
    for (void* b : bufs)
       if (b)
          cudaFree(b);

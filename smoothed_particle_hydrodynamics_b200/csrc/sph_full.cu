@@ -1376,32 +1376,47 @@ __device__ __forceinline__ void density_pairs_packed(const DevParams& P, const S
 }
 #endif
 
+// One 8x8x4 tile of the density sweep.  Fast path: the layout of the whole tile is set up at once and, when its
+// halo fits the staging buffer (always, outside dense clumps), staged and swept; otherwise warp 0 picks the
+// sub-division level from the cell table (choose_level) and the sub-tiles are done one after the other.
 template <bool UNIT, bool UMASS>
-__global__ void __launch_bounds__(kTileThreads, kTileCtas)
-   k_density_tiled(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ cell_start,
-                   const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ vel4,
-                   float4* __restrict__ s_posA4, float4* __restrict__ s_velB4, float* __restrict__ s_rho,
-                   uint2* __restrict__ hit_rec, unsigned* __restrict__ hit_info)
+__device__ __forceinline__ void density_tile(const DevParams& P, int X0, int Y0, int Z0, TileLayout& L, int& s_level,
+                                             float* sg, const float4* __restrict__ s_pos4,
+                                             const uint32_t* __restrict__ cell_start,
+                                             const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ vel4,
+                                             float4* __restrict__ s_posA4, float4* __restrict__ s_velB4,
+                                             float* __restrict__ s_rho, uint2* __restrict__ hit_rec,
+                                             unsigned* __restrict__ hit_info)
 {
-   extern __shared__ __align__(16) unsigned char smem_raw[];
-   float* sg = reinterpret_cast<float*>(smem_raw);
-   __shared__ TileLayout L;
-   __shared__ int s_level, s_pop;
-   int X0, Y0, Z0;
-   tile_origin(X0, Y0, Z0);
-   if (threadIdx.x < 32)
+   const int cap = UMASS ? kCap : kCapMass;
    {
-      int pop = tile_population(P, X0, Y0, Z0, cell_start);
-      int level = pop > 0 ? choose_level(P, X0, Y0, Z0, cell_start, UMASS ? kCap : kCapMass) : 0;
-      if (threadIdx.x == 0)
+      const SubTile t = {X0, Y0, Z0, TBX, TBY, TBZ};
+      setup_layout(P, t, cell_start, true, L);
+      if (L.ntargets == 0)
+         return;
+      if (L.total <= cap)
       {
-         s_pop = pop;
-         s_level = level;
+         stage_rows_packed<UMASS>(P, t, L, s_pos4, sg);
+         __syncthreads();
+#if SPH_DENS_PAIR
+         density_pairs_packed<UNIT, UMASS>(P, t, L, sg, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho, hit_rec,
+                                           hit_info);
+#else
+         density_targets_packed<UNIT, UMASS>(P, t, L, sg, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho, hit_rec,
+                                             hit_info);
+#endif
+         return;
       }
    }
+   // dense tile: sub-divide (levels 1-3) or, past that, sweep from global memory (level 4)
    __syncthreads();
-   if (s_pop == 0)
-      return;
+   if (threadIdx.x < 32)
+   {
+      int level = choose_level(P, X0, Y0, Z0, cell_start, cap);
+      if (threadIdx.x == 0)
+         s_level = level < 1 ? 1 : level;      // (level 0 was just ruled out with the exact padded size)
+   }
+   __syncthreads();
    const int level = s_level;
    const int bz = (level >= 1 && level < 4) ? TBZ / 2 : TBZ;
    const int by = (level >= 2 && level < 4) ? TBY / 2 : TBY;
@@ -1432,6 +1447,91 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtas)
             }
             __syncthreads();   // smem and layout are reused by the next sub-tile
          }
+}
+
+// the non-empty tiles of this step: one thread per tile adds up its 32 cell rows in the cell table
+__global__ void __launch_bounds__(256)
+   k_tile_list(DevParams P, int tx, int ty, int tz, const uint32_t* __restrict__ cell_start,
+               uint32_t* __restrict__ tile_list, int* __restrict__ tile_ctl)
+{
+   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   if (i >= tx * ty * tz)
+      return;
+   const int x = i % tx, y = (i / tx) % ty, z = i / (tx * ty);
+   const int X0 = x * TBX, Y0 = y * TBY, Z0 = z * TBZ;
+   int pop = 0;
+   for (int r = 0; r < TROWS; r++)
+   {
+      const int cy = Y0 + r % TBY, cz = Z0 + r / TBY;
+      if (cy < P.fy && cz < P.fz)
+      {
+         const int row = (cz * P.fy + cy) * P.fx;
+         pop += (int)__ldg(&cell_start[row + min(X0 + TBX, P.fx)]) - (int)__ldg(&cell_start[row + X0]);
+      }
+   }
+   if (pop > 0)
+      tile_list[atomicAdd(&tile_ctl[0], 1)] = (uint32_t)x | ((uint32_t)y << 10) | ((uint32_t)z << 20);
+}
+
+#ifndef SPH_DENS_PERSIST
+#define SPH_DENS_PERSIST 1       // 1: persistent CTAs take the non-empty tiles from a list (k_tile_list) instead of one CTA
+                                 // per tile of the grid (83 % of the 40 960 tiles of the 16.7 M dam-break are empty)
+#endif
+
+// Density sweep, persistent form: two CTAs per SM, each takes the next non-empty tile from the list until it is
+// exhausted.  The order in which tiles are taken does not matter: every particle's result is its own.
+template <bool UNIT, bool UMASS>
+__global__ void __launch_bounds__(kTileThreads, kTileCtas)
+   k_density_persist(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ cell_start,
+                     const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ vel4,
+                     float4* __restrict__ s_posA4, float4* __restrict__ s_velB4, float* __restrict__ s_rho,
+                     uint2* __restrict__ hit_rec, unsigned* __restrict__ hit_info,
+                     const uint32_t* __restrict__ tile_list, int* __restrict__ tile_ctl)
+{
+   extern __shared__ __align__(16) unsigned char smem_raw[];
+   float* sg = reinterpret_cast<float*>(smem_raw);
+   __shared__ TileLayout L;
+   __shared__ int s_level, s_tile;
+   for (;;)
+   {
+      if (threadIdx.x == 0)
+         s_tile = atomicAdd(&tile_ctl[1], 1);
+      __syncthreads();
+      const int ti = s_tile;
+      if (ti >= tile_ctl[0])      // (final: k_tile_list ran before this kernel)
+         return;
+      const uint32_t code = __ldg(&tile_list[ti]);
+      density_tile<UNIT, UMASS>(P, (int)(code & 1023u) * TBX, (int)((code >> 10) & 1023u) * TBY,
+                                (int)(code >> 20) * TBZ, L, s_level, sg, s_pos4, cell_start, idx_sorted, vel4,
+                                s_posA4, s_velB4, s_rho, hit_rec, hit_info);
+      __syncthreads();            // the layout, the staging buffer and s_tile are reused
+   }
+}
+
+template <bool UNIT, bool UMASS>
+__global__ void __launch_bounds__(kTileThreads, kTileCtas)
+   k_density_tiled(DevParams P, const float4* __restrict__ s_pos4, const uint32_t* __restrict__ cell_start,
+                   const uint32_t* __restrict__ idx_sorted, const float4* __restrict__ vel4,
+                   float4* __restrict__ s_posA4, float4* __restrict__ s_velB4, float* __restrict__ s_rho,
+                   uint2* __restrict__ hit_rec, unsigned* __restrict__ hit_info)
+{
+   extern __shared__ __align__(16) unsigned char smem_raw[];
+   float* sg = reinterpret_cast<float*>(smem_raw);
+   __shared__ TileLayout L;
+   __shared__ int s_level, s_pop;
+   int X0, Y0, Z0;
+   tile_origin(X0, Y0, Z0);
+   if (threadIdx.x < 32)
+   {
+      int pop = tile_population(P, X0, Y0, Z0, cell_start);
+      if (threadIdx.x == 0)
+         s_pop = pop;
+   }
+   __syncthreads();
+   if (s_pop == 0)
+      return;
+   density_tile<UNIT, UMASS>(P, X0, Y0, Z0, L, s_level, sg, s_pos4, cell_start, idx_sorted, vel4, s_posA4, s_velB4,
+                             s_rho, hit_rec, hit_info);
 }
 
 // Force sweep: one thread per cell-sorted particle, no shared-memory staging and
@@ -2127,6 +2227,24 @@ int sph_full_configure(sphb200_ctx* ctx)
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem()));
    SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_tiled<false, false>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem()));
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_persist<true, true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem()));
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_persist<true, false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem()));
+   SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_density_persist<false, false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density_smem()));
+   {
+      cudaDeviceProp prop;
+      SPH_CUDA_CHECK(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+      ctx->sm_count = prop.multiProcessorCount;
+      if (1023 * TBX < 2 * ctx->params.grid_x || 1023 * TBY < 2 * ctx->params.grid_y || 4095 * TBZ < 2 * ctx->params.grid_z)
+         return sph_fail(ctx, SPHB200_E_INVALID, "FULL mode: grid too large for the tile list encoding");
+      if (!ctx->tile_list)
+      {
+         SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->tile_list, sizeof(uint32_t) * (size_t)sph_full_tile_count(ctx)));
+         SPH_CUDA_CHECK(ctx, cudaMalloc((void**)&ctx->tile_ctl, 2 * sizeof(int)));
+      }
+   }
    SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_force_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)force_smem()));
    SPH_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_force_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2191,12 +2309,27 @@ int sph_step_full(sphb200_ctx* ctx)
    if (tiled)
    {
       dim3 tiles((P.fx + TBX - 1) / TBX, (P.fy + TBY - 1) / TBY, (P.fz + TBZ - 1) / TBZ);   // local grid
+#if SPH_DENS_PERSIST
+      const int ntiles = (int)(tiles.x * tiles.y * tiles.z);
+      SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->tile_ctl, 0, 2 * sizeof(int), st));
+      k_tile_list<<<(ntiles + 255) / 256, 256, 0, st>>>(P, (int)tiles.x, (int)tiles.y, (int)tiles.z, ctx->cell_start,
+                                                        ctx->tile_list, ctx->tile_ctl);
+      ctx->launches++;
+      auto kd = k_density_persist<false, false>;
+      if (P.scale == 1.0f)
+         kd = ctx->uniform_mass ? k_density_persist<true, true> : k_density_persist<true, false>;
+      const int ctas = min(ntiles, kTileCtas * ctx->sm_count);
+      kd<<<ctas, kTileThreads, density_smem(), st>>>(P, ctx->s_pos4, ctx->cell_start, ctx->idx_order, ctx->vel4,
+                                                    ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->hit_rec,
+                                                    ctx->hit_info, ctx->tile_list, ctx->tile_ctl);
+#else
       auto kd = k_density_tiled<false, false>;
       if (P.scale == 1.0f)
          kd = ctx->uniform_mass ? k_density_tiled<true, true> : k_density_tiled<true, false>;
       kd<<<tiles, kTileThreads, density_smem(), st>>>(P, ctx->s_pos4, ctx->cell_start, ctx->idx_order, ctx->vel4,
                                                      ctx->s_posA4, ctx->s_velB4, ctx->s_rho, ctx->hit_rec,
                                                      ctx->hit_info);
+#endif
    }
    else
       k_density_flat<<<(n + kFlatThreads - 1) / kFlatThreads, kFlatThreads, 0, st>>>(

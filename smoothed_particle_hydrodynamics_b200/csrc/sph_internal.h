@@ -128,6 +128,9 @@ struct sphb200_ctx
    int* s_count;          // sorted neighbour count
    uint2* hit_rec;        // FULL mode hit-mask stream {mask, smem byte offset}, see sph_full.cu
    unsigned* hit_info;    // per sorted particle: records | hits << 8, or 0xff = scan
+   uint32_t* tile_list;   // density sweep: the non-empty 8x8x4 tiles of this step (x | y << 10 | z << 20, in tiles)
+   int* tile_ctl;         // [0] tiles in the list, [1] next tile to hand out
+   int sm_count;
    cudaTextureObject_t tex_posA, tex_velB;   // linear float4 views of s_posA4 / s_velB4 (force-sweep A/B: TEX path)
 
    // SAMPLED mode / on-demand lists, original order
@@ -215,6 +218,7 @@ int sph_step_sampled(sphb200_ctx* ctx);
 int sph_step_full(sphb200_ctx* ctx);
 int sph_full_build_lists(sphb200_ctx* ctx, bool from_stream = false);
 int sph_full_configure(sphb200_ctx* ctx);
+int sph_full_tile_count(const sphb200_ctx* ctx);
 // sph_reduce.cu (in sph_grid.cu)
 int sph_reset_scalars(sphb200_ctx* ctx);
 int sph_finish_scalars(sphb200_ctx* ctx, int blocks);
