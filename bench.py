@@ -393,7 +393,7 @@ def roofline_block(job, phase, clocks, hbm, peak_kind):
                        "pipe are far from saturated: DESIGN.md section 5"}
     else:
         dom = {"key": "density", "ms": dens_ms, "bytes": ALG_BYTES_DENSITY, "bound": "fp32",
-               "kernel": "k_density_tiled (density + EOS + hit-mask stream sweep, packed FP32)",
+               "kernel": "k_density_persist (density + EOS + hit-mask stream sweep, packed FP32, x-trimmed runs)",
                "note": "bound by the FP32 pipe / instruction issue (ncu: FMA pipe cycles, packed f32x2 instructions "
                        "hold the pipe two cycles), not by HBM: DESIGN.md section 5"}
     achieved = dom["bytes"] * job.n / (dom["ms"] * 1e-3) / 1e9 if dom["ms"] > 0 else 0.0
@@ -412,7 +412,7 @@ def roofline_block(job, phase, clocks, hbm, peak_kind):
                 "peak_formula": "148 SMs x 128 lanes x 2 flop x %.0f MHz" % (clk / 1e6)}
     sweeps = [{"kernel": name, "kernel_ms": ms, "alg_bytes_per_particle": b, "achieved": b * job.n / (ms * 1e-3) / 1e9,
                "frac": b * job.n / (ms * 1e-3) / 1e9 / hbm}
-              for name, ms, b in (("k_density_tiled", dens_ms, ALG_BYTES_DENSITY), ("k_force_stream", force_ms, ALG_BYTES_FORCE),
+              for name, ms, b in (("k_tile_list + k_density_persist", dens_ms, ALG_BYTES_DENSITY), ("k_force_stream", force_ms, ALG_BYTES_FORCE),
                                   ("k_cell_keys + scan + k_scatter + k_rank_gather", float(phase[0]),
                                    ALG_BYTES_STEP - ALG_BYTES_DENSITY - ALG_BYTES_FORCE)) if ms > 0]
     return {"bound": dom["bound"], "contract_bound": "hbm", "kernel": dom["kernel"], "sweeps": sweeps,
