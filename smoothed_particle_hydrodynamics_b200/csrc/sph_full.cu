@@ -1449,27 +1449,17 @@ __device__ __forceinline__ void density_tile(const DevParams& P, int X0, int Y0,
          }
 }
 
-// the non-empty tiles of this step: one thread per tile adds up its 32 cell rows in the cell table
+// the non-empty tiles of this step: one warp per tile, one lane per cell row of the tile (cell-table lookups)
 __global__ void __launch_bounds__(256)
    k_tile_list(DevParams P, int tx, int ty, int tz, const uint32_t* __restrict__ cell_start,
                uint32_t* __restrict__ tile_list, int* __restrict__ tile_ctl)
 {
-   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+   const int i = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
    if (i >= tx * ty * tz)
       return;
    const int x = i % tx, y = (i / tx) % ty, z = i / (tx * ty);
-   const int X0 = x * TBX, Y0 = y * TBY, Z0 = z * TBZ;
-   int pop = 0;
-   for (int r = 0; r < TROWS; r++)
-   {
-      const int cy = Y0 + r % TBY, cz = Z0 + r / TBY;
-      if (cy < P.fy && cz < P.fz)
-      {
-         const int row = (cz * P.fy + cy) * P.fx;
-         pop += (int)__ldg(&cell_start[row + min(X0 + TBX, P.fx)]) - (int)__ldg(&cell_start[row + X0]);
-      }
-   }
-   if (pop > 0)
+   const int pop = tile_population(P, x * TBX, y * TBY, z * TBZ, cell_start);
+   if (pop > 0 && (threadIdx.x & 31) == 0)
       tile_list[atomicAdd(&tile_ctl[0], 1)] = (uint32_t)x | ((uint32_t)y << 10) | ((uint32_t)z << 20);
 }
 
@@ -2312,7 +2302,7 @@ int sph_step_full(sphb200_ctx* ctx)
 #if SPH_DENS_PERSIST
       const int ntiles = (int)(tiles.x * tiles.y * tiles.z);
       SPH_CUDA_CHECK(ctx, cudaMemsetAsync(ctx->tile_ctl, 0, 2 * sizeof(int), st));
-      k_tile_list<<<(ntiles + 255) / 256, 256, 0, st>>>(P, (int)tiles.x, (int)tiles.y, (int)tiles.z, ctx->cell_start,
+      k_tile_list<<<(ntiles + 7) / 8, 256, 0, st>>>(P, (int)tiles.x, (int)tiles.y, (int)tiles.z, ctx->cell_start,
                                                         ctx->tile_list, ctx->tile_ctl);
       ctx->launches++;
       auto kd = k_density_persist<false, false>;
