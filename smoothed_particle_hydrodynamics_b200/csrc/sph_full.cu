@@ -1674,6 +1674,10 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    }
    else
    {
+      // (dense scenes: more records per particle than the shared-memory cache holds)
+#pragma unroll 1
+      for (; it < nmin; it += kForceIlp)
+         trip(it, std::false_type(), std::false_type());
 #pragma unroll 1
       for (; it < nmax; it += kForceIlp)
          trip(it, std::true_type(), std::false_type());
