@@ -67,10 +67,6 @@ namespace
 #ifndef SPH_CAP
 #define SPH_CAP 6600
 #endif
-#ifndef SPH_DENS_PAIR
-#define SPH_DENS_PAIR 0          // 1: a thread of the density sweep owns TWO targets of one cell (register blocking:
-                                 // every candidate group is loaded once for both, all run / chunk bookkeeping is shared)
-#endif
 constexpr int kDensUnroll = SPH_DENS_UNROLL;
 constexpr int TBX = 8, TBY = SPH_TBY, TBZ = SPH_TBZ;   // tile extent in fine cells (x rows are contiguous in memory)
 constexpr int HROWS = (TBY + 2) * (TBZ + 2);   // halo rows (y,z) of a full tile
@@ -90,9 +86,6 @@ constexpr int kCapMass = (12 * (kCap + 4)) / 16 - 4;   // ... with per-particle 
 #endif
 constexpr int XQ = SPH_XQ;                      // x thresholds per cell edge
 constexpr int XT = (TBX + 2) * XQ + 2;          // table entries per halo row: thresholds 0 .. (TBX+2)*XQ, + the end
-constexpr int kPairCap = (kCap + TBX * TBY * TBZ) / 2 + 1;   // pairs of a staged tile: sum over cells of ceil(count / 2)
-static_assert(kCap < 32768, "a pair's first target number has 15 bits");
-static_assert(TBX * TBY * TBZ <= kTileThreads, "one thread per target cell builds the pair table");
 constexpr int WCAP = 32;                    // hit-mask records per particle (32 candidates each)
 constexpr unsigned kNoStream = 0xffu;       // info.nw value: no stream, scan instead
 constexpr unsigned kRunShift = 28;          // record base: sorted index | x-run number << 28
@@ -168,7 +161,6 @@ struct TileLayout
    int tgt_off[TROWS + 1];   // prefix of target counts per target row
    int total;                // staged particles
    int ntargets;
-   int next_target;          // packed sweep: the next block of 32 targets a warp may take
    int rowk[TROWS];          // sorted index of target t of row r = rowk[r] + t
 #if SPH_DENS_XTRIM
    ushort2 xtab[HROWS][XT];          // per halo row and x threshold t: .x = where a run may start when its lower bound
@@ -176,14 +168,7 @@ struct TileLayout
                                      // first staged slot whose index is >= t -- unless the row is not ascending in x
                                      // (stage_rows_packed): then .x is the row's start and .y its end (no trimming)
 #endif
-#if SPH_DENS_PAIR
-   int npairs;               // work items of the packed sweep: one or two targets of one cell
-   int wsum[32];
-   unsigned short pcode[kPairCap];   // per pair: lx | r << 4 | hr0 << 9  (its cell)
-   unsigned short ptgt[kPairCap];    // per pair: tile-local number of its first target | (two targets) << 15
-#else
    unsigned short tcell[kCap];   // per target: lx | r << 4 | hr0 << 9  (its cell; see locate_target)
-#endif
 };
 
 // ---- pair arithmetic ---------------------------------------------------------
@@ -338,68 +323,6 @@ __device__ __forceinline__ void force_accumulate(const ForceI& I, const PairTerm
       vt.x = (vt.x + t.wx) * I.s;      // sph.cpp:875-882: scaled inside the loop
       vt.y = (vt.y + t.wy) * I.s;
       vt.z = (vt.z + t.wz) * I.s;
-      count++;
-   }
-}
-
-#ifndef SPH_FORCE_PACK
-#define SPH_FORCE_PACK 0   // 1: the x and y components of the pair body as packed f32x2 operations (A/B: 1.93 against 1.89 ms)
-#endif
-// The pair body with x and y packed (fma / mul / add.rn.f32x2): a float4 record arrives in four consecutive
-// registers, so (x, y) and (vx, vy) are register pairs as loaded.  Every operation is the same single-rounded
-// operation as in force_term: dx = fma(x_j, -1, x_i) is exactly x_i - x_j.
-struct PairTerm2
-{
-   f32x2 pxy, wxy;
-   float pz, wz;
-   int hit;
-};
-
-struct ForceI2     // packed copies of the per-target constants
-{
-   f32x2 xy, vxy, ss, neg1;
-};
-
-template <bool UNIT_SCALE>
-__device__ __forceinline__ PairTerm2 force_term2(const DevParams& P, const ForceI& I, const ForceI2& J, float4 pj,
-                                                 float4 vj, bool not_self)
-{
-   const f32x2 dxy = ffma2(pack2(pj.x, pj.y), J.neg1, J.xy);
-   const float dz = __fsub_rn(I.z, pj.z);
-   float sx, sy;
-   unpack2(fmul2(dxy, dxy), sx, sy);
-   const float d2 = __fadd_rn(__fadd_rn(sx, sy), __fmul_rn(dz, dz));   // sph.cpp:641
-   PairTerm2 t;
-   t.hit = (d2 < P.h2 && not_self) ? 1 : 0;
-   float d = sph_sqrt_approx(d2);
-   float dzs = dz;
-   f32x2 dxys = dxy;
-   if (!UNIT_SCALE)
-   {
-      d *= P.scale;
-      dzs *= P.scale;
-      dxys = fmul2(dxy, pack2(P.scale, P.scale));
-   }
-   const float inv = P.k2 * sph_rcp_approx(d + 0.01f);
-   const float hd = P.hs - d;
-   const float c = (hd * hd) * (I.pi_div * pj.w) * inv;
-   t.pxy = fmul2(dxys, pack2(c, c));
-   t.pz = dzs * c;
-   const float cv = hd * vj.w;
-   t.wxy = fmul2(ffma2(J.vxy, J.neg1, pack2(vj.x, vj.y)), pack2(cv, cv));
-   t.wz = (vj.z - I.vz) * cv;
-   return t;
-}
-
-__device__ __forceinline__ void force_accumulate2(const ForceI& I, const ForceI2& J, const PairTerm2& t, f32x2& pgxy,
-                                                  float& pgz, f32x2& vtxy, float& vtz, int& count)
-{
-   if (t.hit)
-   {
-      pgxy = fadd2(pgxy, t.pxy);
-      pgz += t.pz;
-      vtxy = fmul2(fadd2(vtxy, t.wxy), J.ss);      // sph.cpp:875-882: scaled inside the loop
-      vtz = (vtz + t.wz) * I.s;
       count++;
    }
 }
@@ -637,55 +560,9 @@ __device__ void setup_layout(const DevParams& P, const SubTile& t, const uint32_
       {
          L.tgt_off[trows] = incl;
          L.ntargets = incl;
-         L.next_target = 0;
       }
    }
    __syncthreads();
-#if SPH_DENS_PAIR
-   // pair table (staged tiles hold at most kCap particles): one thread per target cell;
-   // a cell with c particles makes ceil(c / 2) work items, numbered by a block-wide scan
-   {
-      const int trows = t.by * t.bz;
-      const int ncell = trows * t.bx;
-      const int c = threadIdx.x;
-      int pc = 0, t0 = 0, cnt = 0;
-      unsigned short code = 0;
-      if (staged && c < ncell)
-      {
-         int r = c / t.bx, x = c - r * t.bx + 1;
-         int hr0 = (r / t.by + 1) * (t.by + 2) + (r % t.by + 1);
-         int first = L.cs[hr0][1];
-         t0 = L.tgt_off[r] + (L.cs[hr0][x] - first);
-         cnt = L.cs[hr0][x + 1] - L.cs[hr0][x];
-         code = (unsigned short)(x | (r << 4) | (hr0 << 9));
-         pc = (cnt + 1) >> 1;
-         if (x == 1)
-            L.rowk[r] = first - L.tgt_off[r];
-      }
-      int incl = pc;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1)
-      {
-         int up = __shfl_up_sync(0xffffffffu, incl, o);
-         if ((threadIdx.x & 31) >= o)
-            incl += up;
-      }
-      if ((threadIdx.x & 31) == 31)
-         L.wsum[threadIdx.x >> 5] = incl;
-      __syncthreads();
-      int base = incl - pc;
-      for (int w = 0; w < (int)(threadIdx.x >> 5); w++)
-         base += L.wsum[w];
-      for (int i = 0; i < pc; i++)
-      {
-         L.pcode[base + i] = code;
-         L.ptgt[base + i] = (unsigned short)((t0 + 2 * i) | ((2 * i + 1 < cnt) ? 0x8000 : 0));
-      }
-      if (threadIdx.x == blockDim.x - 1)
-         L.npairs = base + pc;
-   }
-   __syncthreads();
-#else
    // target -> cell table (staged tiles hold at most kCap particles): one thread per
    // target cell writes the code of its particles
    const int trows = t.by * t.bz;
@@ -703,7 +580,6 @@ __device__ void setup_layout(const DevParams& P, const SubTile& t, const uint32_
          L.rowk[r] = first - L.tgt_off[r];
    }
    __syncthreads();
-#endif
 }
 
 struct Target
@@ -732,7 +608,6 @@ __device__ __forceinline__ Target locate_target_search(const SubTile& t, const T
    return T;
 }
 
-#if !SPH_DENS_PAIR
 // maps flat target number -> particle and its cell (table built by setup_layout)
 __device__ __forceinline__ Target locate_target(const TileLayout& L, int tnum)
 {
@@ -743,7 +618,6 @@ __device__ __forceinline__ Target locate_target(const TileLayout& L, int tnum)
    T.k = L.rowk[(code >> 4) & 31u] + tnum;
    return T;
 }
-#endif
 
 // picks the sub-division level of this CTA's tile: 0 = whole tile ... 3 = every axis halved,
 // 4 = nothing fits (process from global memory).  Evaluated by warp 0.
@@ -1036,7 +910,6 @@ __device__ __forceinline__ void density_group(unsigned a, f32x2 NX, f32x2 NY, f3
    }
 }
 
-#if !SPH_DENS_PAIR
 template <bool UNIT, bool UMASS>
 __device__ __forceinline__ void density_targets_packed(const DevParams& P, const SubTile& t, TileLayout& L,
                                                        const float* __restrict__ sg,
@@ -1056,25 +929,8 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
    const float inv_q = P.h_times2_inv * (2.0f * XQ);     // XQ / h
    const int m0 = (t.x0 - 1) * XQ, mt = (t.bx + 2) * XQ;
 #endif
-#ifndef SPH_DENS_DYNAMIC
-#define SPH_DENS_DYNAMIC 0       // 1: warps take blocks of 32 targets from a shared counter (A/B: 2.09 against 2.07 ms)
-#endif
-#if SPH_DENS_DYNAMIC
-   for (;;)
-   {
-      int tb = 0;
-      if ((threadIdx.x & 31) == 0)
-         tb = atomicAdd(&L.next_target, 32);
-      tb = __shfl_sync(0xffffffffu, tb, 0);
-      if (tb >= L.ntargets)
-         break;
-      const int tnum = tb + (int)(threadIdx.x & 31);
-      if (tnum >= L.ntargets)
-         continue;
-#else
    for (int tnum = threadIdx.x; tnum < L.ntargets; tnum += blockDim.x)
    {
-#endif
       Target T = locate_target(L, tnum);
       const float4 pi = __ldg(&s_pos4[T.k]);
       const f32x2 NX = pack2(-pi.x, -pi.x), NY = pack2(-pi.y, -pi.y), NZ = pack2(-pi.z, -pi.z);
@@ -1187,194 +1043,7 @@ __device__ __forceinline__ void density_targets_packed(const DevParams& P, const
    }
 }
 
-#endif
 
-#if SPH_DENS_PAIR
-// one group of four candidates against TWO targets (a, b) of one cell: the three LDS.128 are
-// shared, the arithmetic of the two targets is independent (ILP 2)
-template <bool UNIT, bool UMASS, int OFF>
-__device__ __forceinline__ void density_group2(unsigned a, f32x2 NXa, f32x2 NYa, f32x2 NZa, f32x2 NXb, f32x2 NYb,
-                                               f32x2 NZb, f32x2 NH, f32x2 NTHR, f32x2 S2, unsigned& maska,
-                                               unsigned& maskb, f32x2& suma, f32x2& sumb)
-{
-   const ulonglong2 X = lds128<OFF>(a), Y = lds128<OFF + 16>(a), Z = lds128<OFF + 32>(a);
-   ulonglong2 M;
-   if (!UMASS)
-      M = lds128<OFF + 48>(a);
-#pragma unroll
-   for (int half = 0; half < 2; half++)
-   {
-      const f32x2 xs = half ? X.y : X.x, ys = half ? Y.y : Y.x, zs = half ? Z.y : Z.x;
-#pragma unroll
-      for (int tg = 0; tg < 2; tg++)
-      {
-         f32x2 dx = fadd2(xs, tg ? NXb : NXa);
-         f32x2 dy = fadd2(ys, tg ? NYb : NYa);
-         f32x2 dz = fadd2(zs, tg ? NZb : NZa);
-         f32x2 ee;
-         if (UNIT)
-            ee = ffma2(dz, dz, ffma2(dy, dy, ffma2(dx, dx, NH)));
-         else
-            ee = ffma2(ffma2(dz, dz, ffma2(dy, dy, fmul2(dx, dx))), S2, NH);
-         float s0, s1, e0, e1;
-         unpack2(fadd2(ee, NTHR), s0, s1);
-         unsigned& mask = tg ? maskb : maska;
-         mask = __funnelshift_l(__float_as_uint(s0), mask, 1);
-         mask = __funnelshift_l(__float_as_uint(s1), mask, 1);
-         unpack2(ee, e0, e1);
-         f32x2 u = pack2(fminf(e0, 0.0f), fminf(e1, 0.0f));
-         f32x2& acc = tg ? sumb : suma;
-         if (UMASS)
-            acc = ffma2(fmul2(u, u), u, acc);
-         else
-            acc = ffma2(fmul2(half ? M.y : M.x, u), fmul2(u, u), acc);
-      }
-   }
-}
-
-// The staged sweep with two targets per thread.  Work item = one or two consecutive targets of
-// ONE cell (pair table of setup_layout): they share the 9 runs, so every chunk / group is set up
-// and loaded once and evaluated against both.  A single target is evaluated twice (the second
-// result is dropped).
-template <bool UNIT, bool UMASS>
-__device__ __forceinline__ void density_pairs_packed(const DevParams& P, const SubTile& t, const TileLayout& L,
-                                                     const float* __restrict__ sg, const float4* __restrict__ s_pos4,
-                                                     const uint32_t* __restrict__ idx_sorted,
-                                                     const float4* __restrict__ vel4, float4* __restrict__ s_posA4,
-                                                     float4* __restrict__ s_velB4, float* __restrict__ s_rho,
-                                                     uint2* __restrict__ hit_rec, unsigned* __restrict__ hit_info)
-{
-   constexpr int GF = UMASS ? 12 : 16;   // floats per group
-   const float scale2 = P.scale * P.scale;
-   const float thr = 1e-5f * P.hs2;
-   const f32x2 NH = pack2(-P.hs2, -P.hs2), NTHR = pack2(-thr, -thr), S2 = pack2(scale2, scale2);
-   const unsigned sbase = (unsigned)__cvta_generic_to_shared(sg);
-   const int rowstep = t.by + 2;
-#if SPH_DENS_XTRIM
-   const float inv_q = P.h_times2_inv * (2.0f * XQ);     // XQ / h
-   const int m0 = (t.x0 - 1) * XQ, mt = (t.bx + 2) * XQ;
-#endif
-   for (int pn = threadIdx.x; pn < L.npairs; pn += blockDim.x)
-   {
-      const unsigned code = L.pcode[pn], tg = L.ptgt[pn];
-      const int lx = (int)(code & 15u), hr0 = (int)(code >> 9);
-      const bool two = (tg & 0x8000u) != 0u;
-      const int ka = L.rowk[(code >> 4) & 31u] + (int)(tg & 0x7fffu);
-      const int kb = two ? ka + 1 : ka;
-      const float4 pa = __ldg(&s_pos4[ka]), pb = __ldg(&s_pos4[kb]);
-      const f32x2 NXa = pack2(-pa.x, -pa.x), NYa = pack2(-pa.y, -pa.y), NZa = pack2(-pa.z, -pa.z);
-      const f32x2 NXb = pack2(-pb.x, -pb.x), NYb = pack2(-pb.y, -pb.y), NZb = pack2(-pb.z, -pb.z);
-      uint2* reca = hit_rec + stream_base(ka);
-      uint2* recb = hit_rec + stream_base(kb);
-      f32x2 suma = pack2(0.0f, 0.0f), sumb = pack2(0.0f, 0.0f);
-      int nwa = 0, nwb = 0, nhita = 0, nhitb = 0;
-      // the 9 runs in ascending row order: (z-1: y-1, y, y+1), (z: ...), (z+1: ...)
-      const int* csp = &L.cs[hr0 - rowstep - 1][lx - 1];
-      const int* dlp = &L.row_delta[hr0 - rowstep - 1];
-#if SPH_DENS_XTRIM
-      // the window of the pair: from the lower target's x - w to the upper target's x + w (see density_targets_packed)
-      const float w = 1.001f * P.h;
-      const int mlo = x_threshold(fminf(pa.x, pb.x) - w, inv_q, m0, mt);
-      const int mhi = max(x_threshold(fmaxf(pa.x, pb.x) + w, inv_q, m0 - 1, mt + 1), 1);
-      const ushort2* xtp = &L.xtab[hr0 - rowstep - 1][0];
-#endif
-#pragma unroll kDensUnroll
-      for (int r = 0; r < 9; r++)
-      {
-         const int delta = dlp[0];
-#if SPH_DENS_XTRIM
-         const int b = max(csp[0] + delta, (int)xtp[mlo].x);
-         const int e = min(csp[3] + delta, (int)xtp[mhi].y);
-#else
-         const int b = csp[0] + delta;
-         const int e = csp[3] + delta;
-#endif
-         const bool last_of_plane = (r == 2 || r == 5);
-         csp += last_of_plane ? (rowstep - 2) * CSW : CSW;
-         dlp += last_of_plane ? rowstep - 2 : 1;
-#if SPH_DENS_XTRIM
-         xtp += last_of_plane ? (rowstep - 2) * XT : XT;
-#endif
-#pragma unroll 1
-         for (int c0 = b & ~3; c0 < e; c0 += 32)
-         {
-            const int ng = min(8, (e - c0 + 3) >> 2);
-            const unsigned a0 = sbase + (unsigned)((c0 >> 2) * (GF * 4));   // the chunk's first group
-            unsigned maska = 0, maskb = 0;
-#define SPH_GROUP(N)                                                                                               \
-   density_group2<UNIT, UMASS, (N) * GF * 4>(a0, NXa, NYa, NZa, NXb, NYb, NZb, NH, NTHR, S2, maska, maskb, suma, sumb)
-            SPH_GROUP(0);
-            if (ng > 1)
-            {
-               SPH_GROUP(1);
-               if (ng > 2)
-               {
-                  SPH_GROUP(2);
-                  if (ng > 3)
-                  {
-                     SPH_GROUP(3);
-                     if (ng > 4)
-                     {
-                        SPH_GROUP(4);
-                        if (ng > 5)
-                        {
-                           SPH_GROUP(5);
-                           if (ng > 6)
-                           {
-                              SPH_GROUP(6);
-                              if (ng > 7)
-                                 SPH_GROUP(7);
-                           }
-                        }
-                     }
-                  }
-               }
-            }
-#undef SPH_GROUP
-            // keep the candidates of the run proper, [b, e) (see density_targets_packed)
-            const unsigned keep = (0xffffffffu >> max(b - c0, 0)) & __funnelshift_rc(0u, 0xffffffffu, e - c0);
-            const int sh = 32 - 4 * ng;
-            maska = (maska << sh) & keep;
-            maskb = (maskb << sh) & keep;
-            const unsigned base = (unsigned)(c0 - delta) | ((unsigned)r << 28);
-            if (maska != 0u)
-            {
-               if (nwa < WCAP)
-                  SPH_ST_ONCE(&reca[(size_t)nwa * 32], make_uint2(maska, base));
-               nwa++;
-               nhita += __popc(maska);
-            }
-            if (maskb != 0u)
-            {
-               if (two && nwb < WCAP)
-                  SPH_ST_ONCE(&recb[(size_t)nwb * 32], make_uint2(maskb, base));
-               nwb++;
-               nhitb += __popc(maskb);
-            }
-         }
-      }
-#pragma unroll
-      for (int tgt = 0; tgt < 2; tgt++)
-      {
-         if (tgt && !two)
-            break;
-         const int k = tgt ? kb : ka;
-         const float4 pi = tgt ? pb : pa;
-         const int nw = tgt ? nwb : nwa, nhits = tgt ? nhitb : nhita;
-         SPH_ST_ONCE(&hit_info[k], nw <= WCAP ? ((unsigned)nw | ((unsigned)nhits << 8)) : kNoStream);
-         float sa, sb;
-         unpack2(tgt ? sumb : suma, sa, sb);
-         const float sum = -(sa + sb);
-         // the particle itself sat in the centre run with e = -hs2: remove its own term (the
-         // reference skips realIndex == particleIndex, sph.cpp:737); a NaN or infinite position has term 0
-         float t_self = (pi.x - pi.x == 0.0f && pi.y - pi.y == 0.0f && pi.z - pi.z == 0.0f) ? P.hs2 : 0.0f;   // (inf - inf is NaN too)
-         float self = UMASS ? (t_self * t_self) * t_self : __fmul_rn(pi.w * t_self, t_self * t_self);
-         float rho = UMASS ? (P.k1 * pi.w) * (sum - self) : P.k1 * (sum - self);
-         density_store(P, k, pi, rho, idx_sorted, vel4, s_posA4, s_velB4, s_rho);
-      }
-   }
-}
-#endif
 
 // One 8x8x4 tile of the density sweep.  Fast path: the layout of the whole tile is set up at once and, when its
 // halo fits the staging buffer (always, outside dense clumps), staged and swept; otherwise warp 0 picks the
@@ -1398,13 +1067,8 @@ __device__ __forceinline__ void density_tile(const DevParams& P, int X0, int Y0,
       {
          stage_rows_packed<UMASS>(P, t, L, s_pos4, sg);
          __syncthreads();
-#if SPH_DENS_PAIR
-         density_pairs_packed<UNIT, UMASS>(P, t, L, sg, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho, hit_rec,
-                                           hit_info);
-#else
          density_targets_packed<UNIT, UMASS>(P, t, L, sg, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho, hit_rec,
                                              hit_info);
-#endif
          return;
       }
    }
@@ -1433,13 +1097,8 @@ __device__ __forceinline__ void density_tile(const DevParams& P, int X0, int Y0,
                {
                   stage_rows_packed<UMASS>(P, t, L, s_pos4, sg);
                   __syncthreads();
-#if SPH_DENS_PAIR
-                  density_pairs_packed<UNIT, UMASS>(P, t, L, sg, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho,
-                                                    hit_rec, hit_info);
-#else
                   density_targets_packed<UNIT, UMASS>(P, t, L, sg, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho,
                                                       hit_rec, hit_info);
-#endif
                }
                else
                   density_targets<false, UNIT, UMASS>(P, t, L, s_pos4, idx_sorted, vel4, s_posA4, s_velB4, s_rho,
@@ -1577,10 +1236,6 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
    }
    ForceI I = make_force_i(P, pi, vi, rho_i);
    Vec3 pg = {0.0f, 0.0f, 0.0f}, vt = {0.0f, 0.0f, 0.0f};
-#if SPH_FORCE_PACK
-   const ForceI2 J = {pack2(I.x, I.y), pack2(I.vx, I.vy), pack2(I.s, I.s), pack2(-1.0f, -1.0f)};
-   f32x2 pgxy = pack2(0.0f, 0.0f), vtxy = pack2(0.0f, 0.0f);
-#endif
    int count = 0;
    int w = 0;
    unsigned m = 0;
@@ -1642,15 +1297,6 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
          vj[q] = tex_v ? tex1Dfetch<float4>(tex_velB, j[q]) : __ldg(&s_velB4[j[q]]);
 #endif
       }
-#if SPH_FORCE_PACK
-      PairTerm2 t[kForceIlp];
-#pragma unroll
-      for (int q = 0; q < kForceIlp; q++)
-         t[q] = force_term2<UNIT_SCALE>(P, I, J, pj[q], vj[q], j[q] != kk);
-#pragma unroll
-      for (int q = 0; q < kForceIlp; q++)
-         force_accumulate2(I, J, t[q], pgxy, pg.z, vtxy, vt.z, count);
-#else
       PairTerm t[kForceIlp];
 #pragma unroll
       for (int q = 0; q < kForceIlp; q++)
@@ -1658,7 +1304,6 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
 #pragma unroll
       for (int q = 0; q < kForceIlp; q++)
          force_accumulate(I, t[q], pg, vt, count);
-#endif
    };
    const int nmax = __reduce_max_sync(0xffffffffu, nhits);
    const int nmin = (__reduce_min_sync(0xffffffffu, nhits) / kForceIlp) * kForceIlp;
@@ -1682,10 +1327,6 @@ __global__ void __launch_bounds__(kForceThreads, SPH_FORCE_CTAS)
       for (; it < nmax; it += kForceIlp)
          trip(it, std::true_type(), std::false_type());
    }
-#if SPH_FORCE_PACK
-   unpack2(pgxy, pg.x, pg.y);
-   unpack2(vtxy, vt.x, vt.y);
-#endif
    if (scan && active)
    {
       int b[9], e[9];
