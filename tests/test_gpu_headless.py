@@ -57,3 +57,27 @@ def test_facade_readback_path():
     assert r.returncode == 0, r.stdout + r.stderr
     for name in ("mirror_positions", "grid_counts", "grid_members", "readback_cost", "gravity_row_live"):
         assert "PASS " + name in r.stdout, r.stdout
+
+
+def test_bench_line_contract():
+    """bench.py prints ONE json line with the keys the driver reads (metric / value / e2e / roofline / clocks /
+    gpu_launches / cpu_baseline), on the small dam-break so that the test stays short."""
+    import json
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "dambreak_1m", "--steps", "5",
+                        "--warmup", "3", "--no-extras", "--no-cpu-baseline"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["metric"] == "particle-updates/sec" and d["unit"] == "particle-updates/s" and d["higher_is_better"] is True
+    assert d["n_gpus"] == 1 and d["steps"] == 5 and d["warmup"] == 3 and d["dtype"] == "f32" and d["data"] == "synthetic"
+    assert d["value"] > 1e8 and abs(d["value"] - 1048576 / (d["ms_per_step"] * 1e-3)) < 1e-3 * d["value"]
+    assert d["gpu_launches"] >= 5 * 9
+    e = d["e2e"]
+    assert 0 < e["value"] < d["value"] and e["h2d_bytes_per_step"] == 28 * 1048576 and e["d2h_bytes_per_step"] == 24 * 1048576
+    rf = d["roofline"]
+    assert rf["bound"] in ("fp32", "l1") and rf["unit"] == "GB/s" and 0 < rf["frac"] < 1 and rf["peak"] > 1000
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and len(rf["sweeps"]) == 3
+    assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert "workload" in d["config"] and "dambreak_1m" in d["config"]["workload"] and "model" not in d["config"]
